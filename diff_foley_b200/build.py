@@ -1,0 +1,61 @@
+"""Builds diff_foley_b200/csrc/libdfb.so with nvcc for sm_100a (cross-compiles without a GPU).
+
+The library is built IN-TREE so it travels to the GPU box with the repo snapshot; nothing is
+JIT-compiled at run time.  `python -m diff_foley_b200.build` rebuilds when a source is newer.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(CSRC, "libdfb.so")
+SOURCES = ["igemm_tcgen05.cu", "norm.cu", "attention.cu", "elementwise.cu", "engine.cu", "capi.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",
+    "-Xptxas", "-v",
+]
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    for f in os.listdir(CSRC):
+        if f.endswith((".cu", ".cuh", ".h")) and os.path.getmtime(os.path.join(CSRC, f)) > t:
+            return True
+    inc = os.path.join(HERE, "..", "include", "dfb.h")
+    return os.path.getmtime(inc) > t
+
+
+def build(force=False, verbose=False):
+    if not force and not _stale():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    log = []
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"==== {src}\n{out}")
+        failed |= p.returncode != 0
+    with open(os.path.join(CSRC, "build.log"), "w") as f:
+        f.write("\n".join(log))
+    if failed or verbose:
+        sys.stderr.write("\n".join(log))
+    if failed:
+        raise RuntimeError("nvcc failed, see diff_foley_b200/csrc/build.log")
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

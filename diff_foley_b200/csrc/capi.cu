@@ -1,0 +1,140 @@
+// capi.cu -- per-kernel C entry points (include/dfb.h, "per-kernel entry points").  They wrap the
+// same launchers the UNet engine uses, so the parity tests exercise exactly the shipped kernels.
+#include <mutex>
+
+#include "../../include/dfb.h"
+#include "dfb_internal.h"
+
+namespace dfb {
+
+int kernels_init() {
+  static std::once_flag once;
+  static int rc = 0;
+  std::call_once(once, [] {
+    rc = igemm_init();
+    if (!rc) rc = norm_init();
+    if (!rc) rc = attention_init();
+  });
+  return rc;
+}
+
+// scratch for split-K when a GEMM is launched outside an engine (tests, single-op callers)
+static float* g_ws = nullptr;
+static size_t g_ws_bytes = 0;
+static int* g_counters = nullptr;
+static const int g_ncounters = 1 << 16;
+
+static int ensure_scratch(size_t bytes) {
+  if (g_counters == nullptr) {
+    DFB_CUDA_OK(cudaMalloc((void**)&g_counters, g_ncounters * sizeof(int)));
+    DFB_CUDA_OK(cudaMemset(g_counters, 0, g_ncounters * sizeof(int)));
+  }
+  if (bytes > g_ws_bytes) {
+    if (g_ws) cudaFree(g_ws);
+    g_ws = nullptr;
+    g_ws_bytes = 0;
+    DFB_CUDA_OK(cudaMalloc((void**)&g_ws, bytes));
+    g_ws_bytes = bytes;
+  }
+  return 0;
+}
+
+static int run_igemm(const __half* a, const __half* w, int N, const IGemmGeom& g, IGemmEpilogue ep,
+                     int splits, cudaStream_t s) {
+  int r = kernels_init();
+  if (r) return r;
+  // worst case workspace: every tile split `splits` (or up to 32) ways
+  const size_t M = (size_t)g.B * g.T * g.H * g.W;
+  const size_t tiles_m = (M + 127) / 128 + 8;
+  const size_t bytes = tiles_m * ((N + 63) / 64) * 64 * 128 * sizeof(float) * (splits > 0 ? splits : 32);
+  r = ensure_scratch(std::min<size_t>(bytes, (size_t)1 << 30));
+  if (r) return r;
+  IGemmPlan plan;
+  r = igemm_plan(&plan, a, w, N, g, ep, splits, g_ws, g_ws_bytes, g_counters, g_ncounters);
+  if (r) return r;
+  return igemm_launch(plan, s);
+}
+
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" {
+
+int dfb_gemm(const void* a, const void* w, int M, int N, int K, const float* bias, const float* residual,
+             int act, float* out_f32, void* out_f16, int splits, void* stream) {
+  if (!a || !w || M < 1 || N < 1 || K < 1) { set_error("dfb_gemm: bad argument"); return DFB_E_INVALID; }
+  IGemmEpilogue ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.out_f32 = out_f32;
+  ep.out_f16 = (__half*)out_f16;
+  ep.ldo = (act == ACT_GEGLU) ? N / 2 : N;
+  ep.bias = bias;
+  ep.residual = residual;
+  ep.ld_res = ep.ldo;
+  ep.act = act;
+  return run_igemm((const __half*)a, (const __half*)w, N, gemm_geom(M, K), ep, splits, (cudaStream_t)stream);
+}
+
+int dfb_conv3x3(const void* a, const void* w, int B, int H, int W, int C, int N, const float* bias,
+                const float* rowvec, const float* residual, int act, float* out_f32, void* out_f16,
+                int splits, void* stream) {
+  if (!a || !w || B < 1 || H < 1 || W < 1) { set_error("dfb_conv3x3: bad argument"); return DFB_E_INVALID; }
+  IGemmEpilogue ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.out_f32 = out_f32;
+  ep.out_f16 = (__half*)out_f16;
+  ep.ldo = N;
+  ep.bias = bias;
+  ep.rowvec = rowvec;
+  ep.ld_rowvec = N;
+  ep.rows_per_sample = H * W;
+  ep.residual = residual;
+  ep.ld_res = N;
+  ep.act = act;
+  return run_igemm((const __half*)a, (const __half*)w, N, conv3x3_geom(B, H, W, C), ep, splits,
+                   (cudaStream_t)stream);
+}
+
+int dfb_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, int HW, const float* gamma,
+                  const float* beta, float eps, int silu, void* out, void* raw, void* stream) {
+  int r = kernels_init();
+  if (r) return r;
+  return groupnorm_launch(src0, C0, src1, C1, B, HW, gamma, beta, eps, silu, (__half*)out, (__half*)raw,
+                          (cudaStream_t)stream);
+}
+
+int dfb_layernorm(const float* src, int rows, int C, const float* gamma, const float* beta, float eps,
+                  void* out, void* stream) {
+  return layernorm_launch(src, rows, C, gamma, beta, eps, (__half*)out, (cudaStream_t)stream);
+}
+
+int dfb_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
+                  int ldo, int B, int heads, int Lq, int Lk, int d, int dpad, float scale, void* stream) {
+  int r = kernels_init();
+  if (r) return r;
+  return attention_launch((const __half*)q, ldq, (const __half*)k, ldk, (const __half*)v, ldv,
+                          (__half*)out, ldo, B, heads, Lq, Lk, d, dpad, scale, (cudaStream_t)stream);
+}
+
+int dfb_temb(const void* t, int t_is_float, int B, int dim, void* out, void* stream) {
+  return temb_launch(t, t_is_float, B, dim, (__half*)out, (cudaStream_t)stream);
+}
+
+int dfb_upsample2x_f16(const float* src, void* dst, int B, int H, int W, int C, void* stream) {
+  return upsample2x_f16_launch(src, (__half*)dst, B, H, W, C, (cudaStream_t)stream);
+}
+
+int dfb_im2col_s2(const float* src, void* dst, int B, int H, int W, int C, void* stream) {
+  return im2col_s2_launch(src, (__half*)dst, B, H, W, C, (cudaStream_t)stream);
+}
+
+int dfb_ddim_step(const float* x, const float* eu, const float* ec, const float* grad, float cfg_scale,
+                  float sqrt_one_minus_at, float sqrt_at, float sqrt_a_prev, float dir_coef,
+                  float grad_coef, float* x_prev, float* pred_x0, size_t n, void* stream) {
+  if (!x || !ec || !x_prev) { set_error("dfb_ddim_step: null argument"); return DFB_E_INVALID; }
+  return ddim_update_launch(x, eu, ec, grad, cfg_scale, sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef,
+                            grad_coef, x_prev, pred_x0, n, (cudaStream_t)stream);
+}
+
+}  // extern "C"

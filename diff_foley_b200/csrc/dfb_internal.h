@@ -1,0 +1,120 @@
+// dfb_internal.h -- host-side declarations shared by the kernels' launchers, the UNet engine and
+// the C ABI (include/dfb.h).  Not installed; the public surface is include/dfb.h only.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace dfb {
+
+// ---------------------------------------------------------------------------- error plumbing
+void set_error(const std::string& msg);
+const char* last_error();
+#define DFB_CUDA_OK(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      ::dfb::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + \
+                       __FILE__ + ":" + std::to_string(__LINE__));                          \
+      return -2;                                                                            \
+    }                                                                                       \
+  } while (0)
+
+// one-time per-process kernel attribute setup (dynamic shared memory opt-in); idempotent
+int kernels_init();
+int igemm_init();
+int norm_init();
+int attention_init();
+
+// ------------------------------------------------------------------- implicit-GEMM (tcgen05)
+// One kernel covers Linear, 1x1 conv, 3x3 conv (9 shifted TMA boxes, zero-filled halo) and the
+// CAVP (3,1,1) temporal conv: the A operand is an fp16 channels-last activation tensor
+// [B,T,H,W,C] read through a 5-D TMA map, the weights are fp16 [N, taps*C] (K-major).
+enum : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GEGLU = 2, ACT_RELU = 3 };
+
+struct IGemmGeom {
+  // activation tensor dims (output spatial dims == input dims; stride-1 "same" convs only)
+  int B, T, H, W, C;
+  // tile box: bb*bt*bh*bw == 128 output positions per M tile
+  int bb, bt, bh, bw;
+  int ntaps;            // 1, 3 (temporal) or 9 (3x3)
+  int8_t dt[9], dh[9], dw[9];
+};
+
+struct IGemmEpilogue {
+  float* out_f32;           // optional [M, ldo]
+  __half* out_f16;          // optional [M, ldo]
+  int ldo;                  // row stride (elements) of the outputs
+  const float* bias;        // optional [N]
+  const float* rowvec;      // optional per-sample vector [B, ld_rowvec] added to every row of sample b
+  int ld_rowvec;
+  int rows_per_sample;      // rows (output positions) per sample, for rowvec
+  const float* residual;    // optional fp32 [M, ld_res]
+  int ld_res;
+  int act;                  // ACT_*
+};
+
+struct IGemmPlan {
+  CUtensorMap tmA, tmW;
+  IGemmGeom g;
+  IGemmEpilogue e;
+  int M, N, K;       // logical sizes: M = B*T*H*W, K = ntaps*C
+  int BN;            // tile N (64 or 128)
+  int tiles_m, tiles_n, splits;
+  float* ws;         // split-K workspace (tiles*splits*128*BN floats) or nullptr when splits==1
+  int* counters;     // per-tile arrival counters (zero-initialised, self-resetting)
+};
+
+// Builds tensor maps + tiling for `A` (fp16 [B,T,H,W,C]) and `Wt` (fp16 [N, ntaps*C]).
+// splits==0 lets the planner pick a split-K factor that fills the 148 SMs.
+int igemm_plan(IGemmPlan* plan, const __half* A, const __half* Wt, int N, const IGemmGeom& g,
+               const IGemmEpilogue& e, int splits, float* ws, size_t ws_bytes, int* counters,
+               int ncounters);
+size_t igemm_ws_bytes(const IGemmPlan& plan);
+int igemm_launch(const IGemmPlan& plan, cudaStream_t stream);
+// convenience geometry for a plain [M,K] x [N,K]^T GEMM
+IGemmGeom gemm_geom(int M, int K);
+// geometry for a 3x3 / pad 1 / stride 1 conv over [B,H,W,C]
+IGemmGeom conv3x3_geom(int B, int H, int W, int C);
+
+// --------------------------------------------------------------------------------- norm kernels
+// GroupNorm(32 groups) over the channel-concatenation of up to two fp32 NHWC sources, optional
+// SiLU, fp16 output [B,HW,C0+C1]; optionally also the raw (un-normalised) fp16 copy.
+int groupnorm_launch(const float* src0, int C0, const float* src1, int C1, int B, int HW,
+                     const float* gamma, const float* beta, float eps, int silu, __half* out,
+                     __half* raw_out, cudaStream_t stream);
+// LayerNorm over the last dim of fp32 [rows, C] -> fp16.
+int layernorm_launch(const float* src, int rows, int C, const float* gamma, const float* beta,
+                     float eps, __half* out, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------- attention
+// q: fp16 rows [B*Lq, ldq] (head h at columns h*dpad), k/v likewise with Lk rows per sample.
+// out: fp16 [B*Lq, ldo], head h at columns h*d (un-padded).
+int attention_launch(const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv,
+                     __half* out, int ldo, int B, int heads, int Lq, int Lk, int d, int dpad,
+                     float scale, cudaStream_t stream);
+
+// -------------------------------------------------------------------------------- elementwise
+int temb_launch(const void* t, int t_is_float, int B, int dim, __half* out, cudaStream_t stream);
+int cast_f16_launch(const float* src, __half* dst, size_t n, cudaStream_t stream);
+int upsample2x_f16_launch(const float* src, __half* dst, int B, int H, int W, int C,
+                          cudaStream_t stream);
+// im2col for 3x3 / pad 1 / stride 2: fp32 NHWC [B,H,W,C] -> fp16 [B*(H/2)*(W/2), 9*C]
+int im2col_s2_launch(const float* src, __half* dst, int B, int H, int W, int C,
+                     cudaStream_t stream);
+// stem conv: x NCHW fp32 [Bsrc,Cin,H,W] (sample b reads x[b % Bsrc]) -> NHWC fp32 [B,H,W,Cout]
+int stem_conv_launch(const float* x, int Bsrc, int B, int Cin, int H, int W, const float* w,
+                     const float* bias, int Cout, float* out, cudaStream_t stream);
+// head conv: fp16 NHWC [B,H,W,C] (already GN+SiLU'd) -> NCHW fp32 [B,Cout,H,W]
+int head_conv_launch(const __half* a, int B, int H, int W, int C, const float* w,
+                     const float* bias, int Cout, float* out, cudaStream_t stream);
+// fused classifier-free-guidance combine + DDIM update (ddim.py:241-273 of the reference)
+int ddim_update_launch(const float* x, const float* eps_uncond, const float* eps_cond,
+                       const float* grad, float cfg_scale, float sqrt_one_minus_at, float sqrt_at,
+                       float sqrt_a_prev, float dir_coef, float grad_coef, float* x_prev,
+                       float* pred_x0, size_t n, cudaStream_t stream);
+
+}  // namespace dfb

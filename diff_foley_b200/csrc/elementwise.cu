@@ -1,0 +1,255 @@
+// elementwise.cu -- the small bandwidth/latency-bound kernels around the tensor-core GEMMs:
+// sinusoidal timestep embedding, fp32->fp16 operand casts (plain, nearest-2x upsample, stride-2
+// im2col), the 4-channel stem / head convolutions at the NCHW<->channels-last boundary, and the
+// fused classifier-free-guidance + DDIM update.
+#include "dfb_internal.h"
+#include "dfb_ptx.cuh"
+
+namespace dfb {
+
+// ---------------------------------------------------------------------------------------------
+// timestep_embedding (reference util.py:151-171): [cos(t*f_j) | sin(t*f_j)], f_j = exp(-ln(1e4) j/half)
+__global__ void temb_kernel(const void* __restrict__ t, int t_is_float, int B, int dim,
+                            __half* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half_dim = dim / 2;
+  if (i >= B * half_dim) return;
+  const int b = i / half_dim, j = i - b * half_dim;
+  const float tv = t_is_float ? reinterpret_cast<const float*>(t)[b]
+                              : (float)reinterpret_cast<const long long*>(t)[b];
+  const float freq = expf(-9.210340371976184f * (float)j / (float)half_dim);
+  const float arg = tv * freq;
+  out[(size_t)b * dim + j] = __float2half_rn(cosf(arg));
+  out[(size_t)b * dim + half_dim + j] = __float2half_rn(sinf(arg));
+  if ((dim & 1) && j == 0) out[(size_t)b * dim + dim - 1] = __float2half_rn(0.f);
+}
+
+int temb_launch(const void* t, int t_is_float, int B, int dim, __half* out, cudaStream_t stream) {
+  const int n = B * (dim / 2);
+  temb_kernel<<<(n + 255) / 256, 256, 0, stream>>>(t, t_is_float, B, dim, out);
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void cast_f16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    const float4 v = src[i];
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&b);
+    dst[i] = u;
+  }
+}
+
+int cast_f16_launch(const float* src, __half* dst, size_t n, cudaStream_t stream) {
+  if (n % 4) {
+    set_error("cast_f16: element count must be a multiple of 4");
+    return -1;
+  }
+  const size_t n4 = n / 4;
+  const int blocks = (int)std::min<size_t>((n4 + 255) / 256, 148 * 8);
+  cast_f16_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(src),
+                                              reinterpret_cast<uint2*>(dst), n4);
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// nearest-neighbour 2x upsample (reference openai_unetmodel.py:116, F.interpolate) fused with the
+// fp16 cast: dst[b, y, x, :] = src[b, y/2, x/2, :]
+__global__ void upsample2x_f16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int B,
+                                      int H, int W, int C4) {
+  const size_t total = (size_t)B * 2 * H * 2 * W * C4;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int c = (int)(i % C4);
+    size_t r = i / C4;
+    const int x = (int)(r % (2 * W)); r /= (2 * W);
+    const int y = (int)(r % (2 * H));
+    const int b = (int)(r / (2 * H));
+    const float4 v = src[(((size_t)b * H + (y >> 1)) * W + (x >> 1)) * C4 + c];
+    const __half2 a = __floats2half2_rn(v.x, v.y), bb = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&bb);
+    dst[i] = u;
+  }
+}
+
+int upsample2x_f16_launch(const float* src, __half* dst, int B, int H, int W, int C,
+                          cudaStream_t stream) {
+  if (C % 4) {
+    set_error("upsample2x: C must be a multiple of 4");
+    return -1;
+  }
+  const size_t total = (size_t)B * 4 * H * W * (C / 4);
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
+  upsample2x_f16_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(src),
+                                                    reinterpret_cast<uint2*>(dst), B, H, W, C / 4);
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// im2col for the three Downsample convs (3x3, stride 2, pad 1; reference openai_unetmodel.py:151):
+// dst[(b, yo, xo), tap*C + c] = src[b, 2*yo + dy - 1, 2*xo + dx - 1, c]  (zero outside)
+__global__ void im2col_s2_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int B, int H,
+                                 int W, int C4) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = (size_t)B * Ho * Wo * 9 * C4;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int c = (int)(i % C4);
+    size_t r = i / C4;
+    const int tap = (int)(r % 9); r /= 9;
+    const int xo = (int)(r % Wo); r /= Wo;
+    const int yo = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    const int y = 2 * yo + tap / 3 - 1, x = 2 * xo + tap % 3 - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y >= 0 && y < H && x >= 0 && x < W) v = src[(((size_t)b * H + y) * W + x) * C4 + c];
+    const __half2 a = __floats2half2_rn(v.x, v.y), bb = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&bb);
+    dst[i] = u;
+  }
+}
+
+int im2col_s2_launch(const float* src, __half* dst, int B, int H, int W, int C, cudaStream_t stream) {
+  if (C % 4 || (H & 1) || (W & 1)) {
+    set_error("im2col_s2: C must be a multiple of 4 and H, W even");
+    return -1;
+  }
+  const size_t total = (size_t)B * (H / 2) * (W / 2) * 9 * (C / 4);
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
+  im2col_s2_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(src),
+                                               reinterpret_cast<uint2*>(dst), B, H, W, C / 4);
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stem: conv3x3(Cin->Cout), pad 1, on the NCHW latent (reference openai_unetmodel.py:519).
+// w is packed [Cin*9, Cout] (k = ci*9 + tap) so consecutive threads (co) read consecutive floats.
+__global__ void stem_conv_kernel(const float* __restrict__ x, int Bsrc, int Cin, int H, int W,
+                                 const float* __restrict__ w, const float* __restrict__ bias, int Cout,
+                                 float* __restrict__ out) {
+  const int pix = blockIdx.x;  // b*H*W + y*W + x
+  const int xq = pix % W, yq = (pix / W) % H, b = pix / (W * H);
+  const int bs = b % Bsrc;
+  extern __shared__ float patch[];  // [Cin*9]
+  for (int i = threadIdx.x; i < Cin * 9; i += blockDim.x) {
+    const int ci = i / 9, tap = i - ci * 9;
+    const int yy = yq + tap / 3 - 1, xx = xq + tap % 3 - 1;
+    patch[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                   ? x[(((size_t)bs * Cin + ci) * H + yy) * W + xx]
+                   : 0.f;
+  }
+  __syncthreads();
+  for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+    float acc = bias[co];
+    for (int i = 0; i < Cin * 9; ++i) acc = fmaf(patch[i], w[(size_t)i * Cout + co], acc);
+    out[(size_t)pix * Cout + co] = acc;
+  }
+}
+
+int stem_conv_launch(const float* x, int Bsrc, int B, int Cin, int H, int W, const float* w,
+                     const float* bias, int Cout, float* out, cudaStream_t stream) {
+  stem_conv_kernel<<<B * H * W, 128, Cin * 9 * sizeof(float), stream>>>(x, Bsrc, Cin, H, W, w, bias,
+                                                                        Cout, out);
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// head: conv3x3(C->Cout<=4), pad 1, channels-last fp16 in, NCHW fp32 out (reference
+// openai_unetmodel.py:685).  One warp per output pixel, lanes split K = 9*C; w packed [Cout,9,C] fp32.
+__global__ void __launch_bounds__(256)
+head_conv_kernel(const __half* __restrict__ a, int B, int H, int W, int C, const float* __restrict__ w,
+                 const float* __restrict__ bias, int Cout, float* __restrict__ out) {
+  const int pix = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pix >= B * H * W) return;
+  const int xq = pix % W, yq = (pix / W) % H, b = pix / (W * H);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int c2n = C >> 1;
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = yq + tap / 3 - 1, xx = xq + tap % 3 - 1;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+    const __half2* ar = reinterpret_cast<const __half2*>(a + (((size_t)b * H + yy) * W + xx) * C);
+    for (int c2 = lane; c2 < c2n; c2 += 32) {
+      const float2 v = __half22float2(ar[c2]);
+#pragma unroll
+      for (int co = 0; co < 4; ++co) {
+        if (co < Cout) {
+          const float2 ww = *reinterpret_cast<const float2*>(w + ((size_t)co * 9 + tap) * C + 2 * c2);
+          acc[co] = fmaf(v.x, ww.x, acc[co]);
+          acc[co] = fmaf(v.y, ww.y, acc[co]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < 4; ++co) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
+  }
+  if (lane < Cout) {
+    const float r = (lane == 0) ? acc[0] : (lane == 1) ? acc[1] : (lane == 2) ? acc[2] : acc[3];
+    out[(((size_t)b * Cout + lane) * H + yq) * W + xq] = r + bias[lane];
+  }
+}
+
+int head_conv_launch(const __half* a, int B, int H, int W, int C, const float* w, const float* bias,
+                     int Cout, float* out, cudaStream_t stream) {
+  if (Cout > 4 || (C & 1)) {
+    set_error("head_conv: Cout must be <= 4 and C even");
+    return -1;
+  }
+  head_conv_kernel<<<(B * H * W + 7) / 8, 256, 0, stream>>>(a, B, H, W, C, w, bias, Cout, out);
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One DDIM step's arithmetic (reference ddim.py:241-245 CFG, :377-380 classifier term, :258-273
+// update), same operation order as the reference and no FMA contraction so the sampler arithmetic
+// itself is bit-compatible with the fp32 host path:
+//   e      = e_u + s (e_c - e_u)            [ - grad_coef * grad ]
+//   x0     = (x - sqrt(1-a_t) e) / sqrt(a_t)
+//   x_prev = sqrt(a_prev) x0 + sqrt(1 - a_prev - sigma^2) e          (eta = 0: no noise term)
+__global__ void ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ eu,
+                                   const float* __restrict__ ec, const float* __restrict__ grad,
+                                   float s, float sqrt_1mat, float sqrt_at, float sqrt_aprev,
+                                   float dir_coef, float grad_coef, float* __restrict__ x_prev,
+                                   float* __restrict__ pred_x0, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float e;
+  if (eu != nullptr)
+    e = __fadd_rn(eu[i], __fmul_rn(s, __fsub_rn(ec[i], eu[i])));
+  else
+    e = ec[i];
+  if (grad != nullptr) e = __fsub_rn(e, __fmul_rn(grad_coef, grad[i]));
+  const float x0 = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(sqrt_1mat, e)), sqrt_at);
+  const float xp = __fadd_rn(__fmul_rn(sqrt_aprev, x0), __fmul_rn(dir_coef, e));
+  x_prev[i] = xp;
+  if (pred_x0 != nullptr) pred_x0[i] = x0;
+}
+
+int ddim_update_launch(const float* x, const float* eps_uncond, const float* eps_cond,
+                       const float* grad, float cfg_scale, float sqrt_one_minus_at, float sqrt_at,
+                       float sqrt_a_prev, float dir_coef, float grad_coef, float* x_prev,
+                       float* pred_x0, size_t n, cudaStream_t stream) {
+  ddim_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+      x, eps_uncond, eps_cond, grad, cfg_scale, sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef,
+      grad_coef, x_prev, pred_x0, n);
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dfb

@@ -1,0 +1,623 @@
+// igemm_tcgen05.cu -- the one tensor-core kernel of the UNet hot path.
+//
+// Implicit GEMM on the 5th-gen tensor cores:  out[m, n] = epilogue( sum_k A[m, k] * Wt[n, k] )
+//   * A is an fp16 channels-last activation tensor [B,T,H,W,C]; an M tile is a 5-D TMA box of 128
+//     output positions x 64 channels, one box per (filter tap, 64-channel slab).  Shifting the box
+//     origin by the tap offset and letting TMA zero-fill out-of-bounds coordinates *is* the pad=1
+//     halo of the 3x3 convolutions -- no im2col buffer, no boundary branches.  A plain Linear /
+//     1x1 conv is the single-tap case with W := M.
+//   * Wt is fp16 [N, taps*C] (K-major), 2-D TMA boxes of BN x 64.
+//   * both operand tiles land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma
+//     consumes directly; accumulators live in TMEM (128 lanes x BN fp32 columns).
+//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+//     warps 2..5 = epilogue (each owns the 32 TMEM lanes of its sub-partition = warp_idx % 4).
+//   * epilogue (fused): + bias[n], + per-sample vector (timestep embedding), + fp32 residual,
+//     SiLU / ReLU / GEGLU gate, fp32 and/or fp16 stores.
+//   * split-K for the weight-streaming-bound deep layers (M <= 128 rows against 30-60 MB of
+//     weights): grid.z CTAs each stream a K range, park their fp32 partial tile in an L2-resident
+//     workspace and the last CTA to arrive (per-tile counter) reduces in fixed split order -- so the
+//     result is deterministic -- and runs the epilogue.
+//
+// Replaces (reference, all library calls): nn.Conv2d 3x3/1x1 (openai_unetmodel.py:204,230,241,
+// 107; attention_openai.py:233,244) and nn.Linear (attention_openai.py:40,60,161-168;
+// openai_unetmodel.py:218-224,507-511).
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+#include "dfb_internal.h"
+#include "dfb_ptx.cuh"
+
+namespace dfb {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 fp16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int IGEMM_THREADS = 192;
+
+struct IGemmKParams {
+  int M, N;
+  int B, T, H, W;
+  int bb, bt, bh, bw;
+  int tw, th, tt;  // tiles along W, H, T (tiles along B implied)
+  int ntaps, kpt;  // taps, 64-channel k-blocks per tap
+  int8_t dt[9], dh[9], dw[9];
+  float* out_f32;
+  __half* out_f16;
+  int ldo;
+  const float* bias;
+  const float* rowvec;
+  int ld_rowvec;
+  int rows_per_sample;
+  const float* residual;
+  int ld_res;
+  int act;
+  int splits;
+  float* ws;
+  int* counters;
+};
+
+template <int BN, int STAGES>
+struct IGemmSmem {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int W_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  // full[STAGES], empty[STAGES], tmem_full, then tmem slot + flag
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;  // slack to align the base to 1024 B
+};
+
+template <int BN>
+__device__ __forceinline__ void epilogue_store_chunk(const IGemmKParams& p, float (&v)[32],
+                                                     bool row_ok, long m, int b, int n_base,
+                                                     int out_col_base, int ncols_valid) {
+  // v: 32 consecutive accumulator columns of this thread's row (already summed over K).
+  if (!row_ok) return;
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols_valid) v[j] += __ldg(p.bias + n_base + j);
+  }
+  if (p.rowvec != nullptr) {
+    const int bs = (p.rows_per_sample > 0) ? (int)(m / p.rows_per_sample) : b;
+    const float* rv = p.rowvec + (long)bs * p.ld_rowvec + n_base;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols_valid) v[j] += __ldg(rv + j);
+  }
+  if (p.residual != nullptr) {
+    const float* rs = p.residual + m * p.ld_res + out_col_base;
+    if (ncols_valid == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 r4 = *reinterpret_cast<const float4*>(rs + j);
+        v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols_valid) v[j] += rs[j];
+    }
+  }
+  if (p.act == ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+  } else if (p.act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (p.out_f32 != nullptr) {
+    float* o = p.out_f32 + m * p.ldo + out_col_base;
+    if (ncols_valid == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols_valid) o[j] = v[j];
+    }
+  }
+  if (p.out_f16 != nullptr) {
+    __half* o = p.out_f16 + m * p.ldo + out_col_base;
+    if (ncols_valid == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        __half2 h0 = __floats2half2_rn(v[j], v[j + 1]);
+        __half2 h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+        __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]);
+        __half2 h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2);
+        u.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(o + j) = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols_valid) o[j] = __float2half_rn(v[j]);
+    }
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(IGEMM_THREADS, 1)
+igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                     const __grid_constant__ CUtensorMap tmW,
+                     const __grid_constant__ IGemmKParams p) {
+  using L = IGemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates
+  const int n0 = blockIdx.x * BN;
+  int tm = blockIdx.y;
+  const int tw_i = tm % p.tw; tm /= p.tw;
+  const int th_i = tm % p.th; tm /= p.th;
+  const int tt_i = tm % p.tt; tm /= p.tt;
+  const int tb_i = tm;
+  const int x0 = tw_i * p.bw, y0 = th_i * p.bh, t0 = tt_i * p.bt, b0 = tb_i * p.bb;
+
+  const int kb_total = p.ntaps * p.kpt;
+  const int kb0 = (int)(((long)blockIdx.z * kb_total) / p.splits);
+  const int kb1 = (int)(((long)(blockIdx.z + 1) * kb_total) / p.splits);
+  const int nkb = kb1 - kb0;
+
+  // ---- one-time setup
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, BN);  // BN fp32 columns x 128 lanes (power of two >= 32)
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const int kb = kb0 + i;
+        const int tap = kb / p.kpt;
+        const int c0 = (kb - tap * p.kpt) * BLOCK_K;
+        uint8_t* sa = smem + s * L::STAGE_BYTES;
+        uint8_t* sw = sa + L::A_BYTES;
+        mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+        tma_load_5d(sa, &tmA, &full_bar[s], c0, x0 + p.dw[tap], y0 + p.dh[tap], t0 + p.dt[tap], b0);
+        tma_load_2d(sw, &tmW, &full_bar[s], kb * BLOCK_K, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================================================== MMA issuer
+    constexpr uint32_t idesc = umma_idesc_f16(BLOCK_M, BN);
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint32_t sw = sa + L::A_BYTES;
+        const uint64_t da = umma_desc_k_sw128(sa);
+        const uint64_t db = umma_desc_k_sw128(sw);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // advancing 16 fp16 (32 B) along K inside the 128-B swizzle row = +2 in the addr field
+          umma_f16_ss(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                      (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+        if (i == nkb - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ========================================================================= epilogue
+    const int sub = warp & 3;          // TMEM sub-partition this warp may read
+    const int r = sub * 32 + lane;     // accumulator row (= TMEM lane) owned by this thread
+    const int w_i = r % p.bw;
+    const int h_i = (r / p.bw) % p.bh;
+    const int t_i = (r / (p.bw * p.bh)) % p.bt;
+    const int b_i = r / (p.bw * p.bh * p.bt);
+    const int x = x0 + w_i, y = y0 + h_i, t = t0 + t_i, b = b0 + b_i;
+    const bool row_ok = (x < p.W) && (y < p.H) && (t < p.T) && (b < p.B);
+    const long m = (((long)b * p.T + t) * p.H + y) * p.W + x;
+    const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
+    const int tile_lin = blockIdx.y * gridDim.x + blockIdx.x;
+    constexpr int NCH = BN / 32;
+    const bool geglu = (p.act == ACT_GEGLU);
+
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+
+    if (p.splits == 1) {
+      if (!geglu) {
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t raw[32];
+          tmem_ld_32x32(taddr + c * 32, raw);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          const int nb = n0 + c * 32;
+          const int valid = min(32, p.N - nb);
+          if (valid > 0) epilogue_store_chunk<BN>(p, v, row_ok, m, b, nb, nb, valid);
+        }
+      } else {
+        // GEGLU: tile columns [0,BN/2) are the value half, [BN/2,BN) the gate half of the same
+        // BN/2 output features (weights were interleaved per tile when packed).
+#pragma unroll 1
+        for (int c = 0; c < NCH / 2; ++c) {
+          uint32_t rv[32], rg[32];
+          tmem_ld_32x32(taddr + c * 32, rv);
+          tmem_ld_32x32(taddr + BN / 2 + c * 32, rg);
+          tmem_ld_wait();
+          if (row_ok) {
+            const int nbv = n0 + c * 32, nbg = n0 + BN / 2 + c * 32;
+            const int ob = blockIdx.x * (BN / 2) + c * 32;
+            __half* o = p.out_f16 + m * p.ldo + ob;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float a0 = __uint_as_float(rv[j]) + __ldg(p.bias + nbv + j);
+              float a1 = __uint_as_float(rv[j + 1]) + __ldg(p.bias + nbv + j + 1);
+              float g0 = __uint_as_float(rg[j]) + __ldg(p.bias + nbg + j);
+              float g1 = __uint_as_float(rg[j + 1]) + __ldg(p.bias + nbg + j + 1);
+              *reinterpret_cast<__half2*>(o + j) =
+                  __floats2half2_rn(a0 * gelu_erf_f(g0), a1 * gelu_erf_f(g1));
+            }
+          }
+        }
+      }
+    } else {
+      // ---- split-K: park the raw partial tile, last arriver reduces + runs the epilogue
+      float* wtile = p.ws + ((long)tile_lin * p.splits) * (BLOCK_M * BN);
+      float* mine = wtile + (long)blockIdx.z * (BLOCK_M * BN) + (long)r * BN;
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32(taddr + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(mine + c * 32 + j) =
+              make_uint4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        const int old = atomicAdd(p.counters + tile_lin, 1);
+        const int last = (old == p.splits - 1) ? 1 : 0;
+        if (last) p.counters[tile_lin] = 0;  // self-reset for the next launch
+        *last_flag = last;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (*last_flag) {
+        __threadfence();
+        const float* rowp = wtile + (long)r * BN;
+        if (!geglu) {
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            for (int s = 0; s < p.splits; ++s) {
+              const float* q = rowp + (long)s * (BLOCK_M * BN) + c * 32;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 f = __ldcg(reinterpret_cast<const float4*>(q + j));
+                v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
+              }
+            }
+            const int nb = n0 + c * 32;
+            const int valid = min(32, p.N - nb);
+            if (valid > 0) epilogue_store_chunk<BN>(p, v, row_ok, m, b, nb, nb, valid);
+          }
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < NCH / 2; ++c) {
+            float a[32], g[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { a[j] = 0.f; g[j] = 0.f; }
+            for (int s = 0; s < p.splits; ++s) {
+              const float* qa = rowp + (long)s * (BLOCK_M * BN) + c * 32;
+              const float* qg = qa + BN / 2;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 f = __ldcg(reinterpret_cast<const float4*>(qa + j));
+                a[j] += f.x; a[j + 1] += f.y; a[j + 2] += f.z; a[j + 3] += f.w;
+                float4 h = __ldcg(reinterpret_cast<const float4*>(qg + j));
+                g[j] += h.x; g[j + 1] += h.y; g[j + 2] += h.z; g[j + 3] += h.w;
+              }
+            }
+            if (row_ok) {
+              const int nbv = n0 + c * 32, nbg = n0 + BN / 2 + c * 32;
+              const int ob = blockIdx.x * (BN / 2) + c * 32;
+              __half* o = p.out_f16 + m * p.ldo + ob;
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                float a0 = a[j] + __ldg(p.bias + nbv + j);
+                float a1 = a[j + 1] + __ldg(p.bias + nbv + j + 1);
+                float g0 = g[j] + __ldg(p.bias + nbg + j);
+                float g1 = g[j + 1] + __ldg(p.bias + nbg + j + 1);
+                *reinterpret_cast<__half2*>(o + j) =
+                    __floats2half2_rn(a0 * gelu_erf_f(g0), a1 * gelu_erf_f(g1));
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// =========================================================================== host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box,
+                  CUtensorMapSwizzle swz) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
+    return -3;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                   gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    std::string s = "cuTensorMapEncodeTiled failed, CUresult=" + std::to_string((int)r) + " rank=" +
+                    std::to_string(rank) + " dims=";
+    for (int i = 0; i < rank; ++i) s += std::to_string((unsigned long long)dims[i]) + ",";
+    s += " box=";
+    for (int i = 0; i < rank; ++i) s += std::to_string(box[i]) + ",";
+    set_error(s);
+    return -3;
+  }
+  return 0;
+}
+
+IGemmGeom gemm_geom(int M, int K) {
+  IGemmGeom g;
+  memset(&g, 0, sizeof(g));
+  g.B = 1; g.T = 1; g.H = 1; g.W = M; g.C = K;
+  g.bb = 1; g.bt = 1; g.bh = 1; g.bw = 128;
+  g.ntaps = 1;
+  return g;
+}
+
+IGemmGeom conv3x3_geom(int B, int H, int W, int C) {
+  IGemmGeom g;
+  memset(&g, 0, sizeof(g));
+  g.B = B; g.T = 1; g.H = H; g.W = W; g.C = C;
+  // 128 output positions per tile: as much of a row as fits, then rows, then samples
+  int bw = std::min(W, 128);
+  while (128 % bw) --bw;  // W is a power of two in this model; keep it general anyway
+  int rem = 128 / bw;
+  int bh = std::min(H, rem);
+  while (rem % bh) --bh;
+  rem /= bh;
+  g.bw = bw; g.bh = bh; g.bt = 1; g.bb = rem;
+  g.ntaps = 9;
+  int i = 0;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      g.dt[i] = 0; g.dh[i] = (int8_t)dy; g.dw[i] = (int8_t)dx;
+      ++i;
+    }
+  return g;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+size_t igemm_ws_bytes(const IGemmPlan& plan) {
+  if (plan.splits <= 1) return 0;
+  return (size_t)plan.tiles_m * plan.tiles_n * plan.splits * BLOCK_M * plan.BN * sizeof(float);
+}
+
+int igemm_plan(IGemmPlan* plan, const __half* A, const __half* Wt, int N, const IGemmGeom& g,
+               const IGemmEpilogue& e, int splits, float* ws, size_t ws_bytes, int* counters,
+               int ncounters) {
+  if (g.C % BLOCK_K != 0) {
+    set_error("igemm: channel count must be a multiple of 64, got " + std::to_string(g.C));
+    return -1;
+  }
+  if (g.bb * g.bt * g.bh * g.bw != BLOCK_M) {
+    set_error("igemm: tile box must cover exactly 128 output positions");
+    return -1;
+  }
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(Wt) & 15)) {
+    set_error("igemm: operand pointers must be 16-byte aligned");
+    return -1;
+  }
+  plan->g = g;
+  plan->e = e;
+  plan->M = g.B * g.T * g.H * g.W;
+  plan->N = N;
+  plan->K = g.ntaps * g.C;
+  const bool geglu = (e.act == ACT_GEGLU);
+  // tile width: 128 unless N is small or 64 divides it better
+  int BN = 128;
+  if (N <= 64 || (N % 128 != 0 && N % 64 == 0 && N < 512)) BN = 64;
+  if (geglu) BN = 128;
+  plan->BN = BN;
+  const int tw = (g.W + g.bw - 1) / g.bw, th = (g.H + g.bh - 1) / g.bh,
+            tt = (g.T + g.bt - 1) / g.bt, tb = (g.B + g.bb - 1) / g.bb;
+  plan->tiles_m = tw * th * tt * tb;
+  plan->tiles_n = (N + BN - 1) / BN;
+  const int tiles = plan->tiles_m * plan->tiles_n;
+  const int kb_total = g.ntaps * (g.C / BLOCK_K);
+  if (splits <= 0) {
+    // fill the machine once: split K until tiles*splits ~ #SMs, keep >= 4 k-blocks per CTA
+    splits = 1;
+    if (tiles < num_sms()) {
+      splits = num_sms() / tiles;
+      splits = std::min(splits, std::max(1, kb_total / 4));
+      splits = std::min(splits, 32);
+      splits = std::max(splits, 1);
+    }
+  }
+  splits = std::min(splits, kb_total);
+  plan->splits = splits;
+  plan->ws = nullptr;
+  plan->counters = nullptr;
+  if (splits > 1) {
+    if (igemm_ws_bytes(*plan) > ws_bytes || tiles > ncounters || ws == nullptr ||
+        counters == nullptr) {
+      set_error("igemm: split-K workspace too small (need " +
+                std::to_string(igemm_ws_bytes(*plan)) + " bytes, " + std::to_string(tiles) +
+                " counters)");
+      return -1;
+    }
+    plan->ws = ws;
+    plan->counters = counters;
+  }
+  if ((e.out_f16 && (e.ldo % 8)) || (e.out_f32 && (e.ldo % 4)) || (e.residual && (e.ld_res % 4)) ||
+      (N % 32) != 0) {
+    set_error("igemm: N must be a multiple of 32 and output/residual row strides 16-byte aligned");
+    return -1;
+  }
+  if (e.out_f16 == nullptr && e.out_f32 == nullptr) {
+    set_error("igemm: no output pointer");
+    return -1;
+  }
+  if (geglu && (e.out_f16 == nullptr || e.bias == nullptr || (N % 128) != 0)) {
+    set_error("igemm: GEGLU epilogue needs fp16 output, bias and N % 128 == 0");
+    return -1;
+  }
+  // ---- tensor maps
+  {
+    uint64_t dims[5] = {(uint64_t)g.C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.T, (uint64_t)g.B};
+    uint64_t str[4];
+    str[0] = (uint64_t)g.C * 2;
+    str[1] = str[0] * g.W;
+    str[2] = str[1] * g.H;
+    str[3] = str[2] * g.T;
+    uint32_t box[5] = {BLOCK_K, (uint32_t)g.bw, (uint32_t)g.bh, (uint32_t)g.bt, (uint32_t)g.bb};
+    int rc = make_tmap_f16(&plan->tmA, A, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)plan->K, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)plan->K * 2};
+    uint32_t box[2] = {BLOCK_K, (uint32_t)BN};
+    int rc = make_tmap_f16(&plan->tmW, Wt, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int igemm_init() {
+  DFB_CUDA_OK(cudaFuncSetAttribute(igemm_tcgen05_kernel<64, 8>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   IGemmSmem<64, 8>::DYN_BYTES));
+  DFB_CUDA_OK(cudaFuncSetAttribute(igemm_tcgen05_kernel<128, 6>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   IGemmSmem<128, 6>::DYN_BYTES));
+  return 0;
+}
+
+template <int BN, int STAGES>
+static int launch_t(const IGemmPlan& plan, const IGemmKParams& kp, cudaStream_t stream) {
+  using L = IGemmSmem<BN, STAGES>;
+  dim3 grid(plan.tiles_n, plan.tiles_m, plan.splits);
+  igemm_tcgen05_kernel<BN, STAGES><<<grid, IGEMM_THREADS, L::DYN_BYTES, stream>>>(plan.tmA,
+                                                                                   plan.tmW, kp);
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int igemm_launch(const IGemmPlan& plan, cudaStream_t stream) {
+  IGemmKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  const IGemmGeom& g = plan.g;
+  kp.M = plan.M; kp.N = plan.N;
+  kp.B = g.B; kp.T = g.T; kp.H = g.H; kp.W = g.W;
+  kp.bb = g.bb; kp.bt = g.bt; kp.bh = g.bh; kp.bw = g.bw;
+  kp.tw = (g.W + g.bw - 1) / g.bw;
+  kp.th = (g.H + g.bh - 1) / g.bh;
+  kp.tt = (g.T + g.bt - 1) / g.bt;
+  kp.ntaps = g.ntaps;
+  kp.kpt = g.C / BLOCK_K;
+  for (int i = 0; i < 9; ++i) { kp.dt[i] = g.dt[i]; kp.dh[i] = g.dh[i]; kp.dw[i] = g.dw[i]; }
+  kp.out_f32 = plan.e.out_f32; kp.out_f16 = plan.e.out_f16; kp.ldo = plan.e.ldo;
+  kp.bias = plan.e.bias; kp.rowvec = plan.e.rowvec; kp.ld_rowvec = plan.e.ld_rowvec;
+  kp.rows_per_sample = plan.e.rows_per_sample;
+  kp.residual = plan.e.residual; kp.ld_res = plan.e.ld_res; kp.act = plan.e.act;
+  kp.splits = plan.splits; kp.ws = plan.ws; kp.counters = plan.counters;
+  if (plan.BN == 64) return launch_t<64, 8>(plan, kp, stream);
+  return launch_t<128, 6>(plan, kp, stream);
+}
+
+}  // namespace dfb

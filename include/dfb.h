@@ -1,0 +1,129 @@
+/* dfb.h -- C ABI of libdfb.so, the B200 (sm_100a) implementation of Diff-Foley's latent-diffusion
+ * sampling hot path.  Plain pointers and sizes only; every pointer named *_dev is a CUDA device
+ * pointer owned by the caller, `stream` is a cudaStream_t passed as void*.  Every function returns
+ * 0 on success and a negative DFB_E* code on failure; dfb_last_error() returns a thread-local
+ * message.  No C++ exceptions cross this boundary and there is no CPU fallback: on a host without an
+ * sm_100 device the compute entry points fail with DFB_E_CUDA.
+ *
+ * Citations are file:line in the reference repository (luosiallen/Diff-Foley @ 0ba1e8ad).
+ */
+#ifndef DFB_H_
+#define DFB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFB_OK 0
+#define DFB_E_INVALID (-1) /* bad argument / unsupported configuration */
+#define DFB_E_CUDA (-2)    /* CUDA runtime error, message has details   */
+#define DFB_E_DRIVER (-3)  /* tensor-map encode / driver entry point    */
+#define DFB_E_STATE (-4)   /* call order (e.g. forward before finalize) */
+
+#define DFB_ACT_NONE 0
+#define DFB_ACT_SILU 1
+#define DFB_ACT_GEGLU 2
+#define DFB_ACT_RELU 3
+
+typedef struct dfb_unet* dfb_handle;
+
+/* Mirrors the constructor arguments of UNetModel that the inference configs use
+ * (diff_foley/modules/diffusionmodules/openai_unetmodel.py:443-469, inference/config/
+ * Stage2_LDM.yaml:21-36).  Unsupported combinations are rejected by dfb_unet_create. */
+typedef struct dfb_unet_cfg {
+  int32_t in_channels;
+  int32_t model_channels;
+  int32_t out_channels;
+  int32_t num_res_blocks;
+  int32_t n_channel_mult;
+  int32_t channel_mult[8];
+  int32_t n_attention_resolutions;
+  int32_t attention_resolutions[8];
+  int32_t num_heads;
+  int32_t context_dim;
+  int32_t latent_h; /* 16 : mel bins / 8   (ddpm.py:1293) */
+  int32_t latent_w; /* 64 : mel frames / 8                 */
+  int32_t max_context_len; /* 32 CAVP frames (notebook cell 13) */
+  int32_t max_batch;       /* largest B_eff (= 2 x clips under classifier-free guidance) */
+} dfb_unet_cfg;
+
+const char* dfb_last_error(void);
+const char* dfb_version(void);
+
+/* ------------------------------------------------------------------ UNet engine (rows a1-a12)
+ * Replaces UNetModel.forward (openai_unetmodel.py:710-742) and everything below it. */
+int dfb_unet_create(const dfb_unet_cfg* cfg, int device, dfb_handle* out);
+/* `name` is the reference state-dict key relative to the UNet (e.g. "input_blocks.1.0.in_layers.2.weight",
+ * demo_util.py:182-184 / SURVEY 3.4); `src_dev` is fp32 on the device in the reference's own layout.
+ * The engine packs it into its fp16 tensor-core layout immediately; the caller may free src after. */
+int dfb_unet_set_weight(dfb_handle h, const char* name, const float* src_dev, const int64_t* shape,
+                        int ndim);
+/* Checks every parameter was supplied and builds the per-batch launch plans lazily. */
+int dfb_unet_finalize(dfb_handle h);
+/* Number of parameter tensors the engine expects; names via dfb_unet_weight_name(i). */
+int dfb_unet_num_weights(dfb_handle h);
+const char* dfb_unet_weight_name(dfb_handle h, int i);
+/* Pre-computes the (step-invariant) cross-attention K/V of all 16 transformer blocks from the
+ * cross-attention context [B_eff, ctx_len, context_dim] fp32 (attention_openai.py:175-176). */
+int dfb_unet_set_context(dfb_handle h, const float* ctx_dev, int b_eff, int ctx_len, void* stream);
+/* eps = UNet(x, t, context).  x/out: fp32 NCHW [b_eff, C, H, W].  t: int64 or fp32 [b_eff].
+ * ctx_dev may be NULL to reuse the K/V of the last dfb_unet_set_context call.
+ * If x has only b_eff/x_repeat distinct samples (CFG feeds cat([x, x])), pass x_repeat = 2 and the
+ * un-duplicated tensor. */
+int dfb_unet_forward(dfb_handle h, const float* x_dev, int x_repeat, const void* t_dev,
+                     int t_is_float, const float* ctx_dev, int ctx_len, float* out_dev, int b_eff,
+                     void* stream);
+/* Whole DDIM loop with classifier-free guidance (ddim.py:179-273): x_T -> x_0 in place.
+ * cond/uncond: fp32 [B, ctx_len, context_dim]; timesteps: host int64[S] in sampling order
+ * (961, 921, ... 1); coefficient arrays are host fp32[S] in the same order:
+ * sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2).  The step is captured once as a CUDA
+ * graph and replayed S times.  pred_x0_dev may be NULL. */
+int dfb_ddim_sample(dfb_handle h, float* x_dev, const float* cond_dev, const float* uncond_dev,
+                    int n_clips, int ctx_len, float cfg_scale, int n_steps, const int64_t* timesteps,
+                    const float* sqrt_one_minus_at, const float* sqrt_at, const float* sqrt_a_prev,
+                    const float* dir_coef, float* pred_x0_dev, void* stream);
+/* kernels launched by the most recent forward / sample call (for bench.py's gpu_launches) */
+long long dfb_unet_last_launch_count(dfb_handle h);
+int dfb_unet_destroy(dfb_handle h);
+
+/* --------------------------------------------------------------- per-kernel entry points
+ * Used by the parity tests (tests/test_ops_gpu.py) and by callers that want single ops. */
+
+/* out[M,N] = act(A[M,K] . W[N,K]^T + bias + residual); A, W fp16 row-major; tcgen05 tensor cores.
+ * splits: 0 = auto split-K, >=1 forced.  (nn.Linear / 1x1 Conv2d) */
+int dfb_gemm(const void* a_f16_dev, const void* w_f16_dev, int M, int N, int K, const float* bias_dev,
+             const float* residual_dev, int act, float* out_f32_dev, void* out_f16_dev, int splits,
+             void* stream);
+/* 3x3 / stride 1 / pad 1 convolution as implicit GEMM; a: fp16 NHWC [B,H,W,C], w: fp16 [N, 9*C]
+ * with k = (ky*3+kx)*C + c; rowvec: optional fp32 [B,N] added per sample (timestep embedding,
+ * openai_unetmodel.py:263-272); residual: optional fp32 NHWC [B,H,W,N]. */
+int dfb_conv3x3(const void* a_f16_dev, const void* w_f16_dev, int B, int H, int W, int C, int N,
+                const float* bias_dev, const float* rowvec_dev, const float* residual_dev, int act,
+                float* out_f32_dev, void* out_f16_dev, int splits, void* stream);
+/* GroupNorm(32) (+SiLU) over concat(src0, src1) channels-last fp32 -> fp16 (util.py:214-216) */
+int dfb_groupnorm(const float* src0_dev, int C0, const float* src1_dev, int C1, int B, int HW,
+                  const float* gamma_dev, const float* beta_dev, float eps, int silu, void* out_f16_dev,
+                  void* raw_f16_dev, void* stream);
+int dfb_layernorm(const float* src_dev, int rows, int C, const float* gamma_dev, const float* beta_dev,
+                  float eps, void* out_f16_dev, void* stream);
+/* softmax(q k^T scale) v per (sample, head) (attention_openai.py:170-193); fp16 in/out */
+int dfb_attention(const void* q_dev, int ldq, const void* k_dev, int ldk, const void* v_dev, int ldv,
+                  void* out_dev, int ldo, int B, int heads, int Lq, int Lk, int d, int dpad, float scale,
+                  void* stream);
+/* sinusoidal timestep embedding (util.py:151-171) -> fp16 [B, dim] */
+int dfb_temb(const void* t_dev, int t_is_float, int B, int dim, void* out_f16_dev, void* stream);
+int dfb_upsample2x_f16(const float* src_dev, void* dst_f16_dev, int B, int H, int W, int C, void* stream);
+int dfb_im2col_s2(const float* src_dev, void* dst_f16_dev, int B, int H, int W, int C, void* stream);
+/* one DDIM update with CFG combine (ddim.py:241-245, 258-273); eps_uncond/grad may be NULL */
+int dfb_ddim_step(const float* x_dev, const float* eps_uncond_dev, const float* eps_cond_dev,
+                  const float* grad_dev, float cfg_scale, float sqrt_one_minus_at, float sqrt_at,
+                  float sqrt_a_prev, float dir_coef, float grad_coef, float* x_prev_dev,
+                  float* pred_x0_dev, size_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFB_H_ */
