@@ -1,0 +1,162 @@
+"""Generates tests/golden/*.npz by running the REFERENCE's own modules (imported unmodified from
+/root/reference through the import shims in tests/golden/_shims) on seeded inputs and seeded
+weights (oracle.unet_oracle.seeded_state_dict).  Run in the build container only:
+
+    python tests/golden/make_golden.py            # all fixtures  (~4 min on 8 vCPU)
+    python tests/golden/make_golden.py small      # just the reduced-width ones
+
+The reference ships no tests or golden vectors of its own, so these files are what pins
+the oracle (oracle/) and, through it and directly, the CUDA path.  Nothing here is read at run time
+on the GPU box except the .npz outputs.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import yaml
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("DIFF_FOLEY_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(HERE, "_shims"))
+sys.path.insert(0, REF)
+
+from oracle import ddim_oracle, unet_oracle  # noqa: E402
+
+torch.manual_seed(0)
+
+
+def ref_unet(cfg):
+    from diff_foley.modules.diffusionmodules.openai_unetmodel import UNetModel
+    m = UNetModel(image_size=32, in_channels=cfg["in_channels"], out_channels=cfg["out_channels"],
+                  model_channels=cfg["model_channels"],
+                  attention_resolutions=list(cfg["attention_resolutions"]),
+                  num_res_blocks=cfg["num_res_blocks"], channel_mult=list(cfg["channel_mult"]),
+                  num_heads=cfg["num_heads"], use_spatial_transformer=True, transformer_depth=1,
+                  context_dim=cfg["context_dim"], use_checkpoint=True, legacy=False)
+    return m.eval()
+
+
+def unet_inputs(cfg, b_eff, seed, t_values):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(b_eff, cfg["in_channels"], cfg["latent_h"], cfg["latent_w"], generator=g)
+    ctx = torch.randn(b_eff, cfg["context_len"], cfg["context_dim"], generator=g)
+    ctx[: b_eff // 2] = 0  # the uncond half of a CFG batch is all-zero context (notebook cell 13)
+    t = torch.tensor(t_values, dtype=torch.long)
+    return x, t, ctx
+
+
+def gen_unet(name, cfg, seed, b_eff, t_values, taps=()):
+    t0 = time.time()
+    sd = unet_oracle.seeded_state_dict(cfg, seed)
+    m = ref_unet(cfg)
+    missing, unexpected = m.load_state_dict(sd, strict=True), None
+    x, t, ctx = unet_inputs(cfg, b_eff, seed + 1000, t_values)
+    acts = {}
+    hooks = []
+    for tap in taps:
+        mod = m.get_submodule(tap)
+        hooks.append(mod.register_forward_hook(lambda _m, _i, o, tap=tap: acts.__setitem__(tap, o.detach().numpy())))
+    with torch.no_grad():
+        eps = m(x, t, context=ctx)
+    for h in hooks:
+        h.remove()
+    out = dict(x=x.numpy(), t=t.numpy(), ctx=ctx.numpy(), eps=eps.numpy(), seed=np.int64(seed))
+    for k, v in acts.items():
+        out["tap:" + k] = v
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: eps absmax {float(eps.abs().max()):.4f} rms {float(eps.pow(2).mean().sqrt()):.4f} "
+          f"({time.time() - t0:.1f}s)")
+
+
+class _StubLDM:
+    """The attributes DDIMSampler touches on the model (ddim.py:15-56, 231-273), around the
+    reference UNet; apply_model has the semantics of ddpm.py:925-1026 for the crossattn key."""
+
+    def __init__(self, unet):
+        self.unet = unet
+        ac = ddim_oracle.alphas_cumprod()
+        betas = torch.linspace(ddim_oracle.LINEAR_START ** 0.5, ddim_oracle.LINEAR_END ** 0.5,
+                               ddim_oracle.NUM_TIMESTEPS, dtype=torch.float64) ** 2
+        self.num_timesteps = ddim_oracle.NUM_TIMESTEPS
+        self.betas = betas.float()
+        self.alphas_cumprod = ac
+        self.alphas_cumprod_prev = torch.cat([torch.ones(1), ac[:-1]])
+        self.device = torch.device("cpu")
+        self.parameterization = "eps"
+
+    def apply_model(self, x, t, c):
+        return self.unet(x, t, context=c)
+
+
+def gen_ddim(name, cfg, seed, n_clips, steps, scale, use_real_ldm=False):
+    """Runs the reference's DDIMSampler.sample (ddim.py:58-113) on CPU."""
+    t0 = time.time()
+    from diff_foley.models.diffusion.ddim import DDIMSampler
+
+    class CpuDDIM(DDIMSampler):  # ddim.py:21-25 hard-codes .to("cuda")
+        def register_buffer(self, name, attr):
+            setattr(self, name, attr)
+
+    sd = unet_oracle.seeded_state_dict(cfg, seed)
+    unet = ref_unet(cfg)
+    unet.load_state_dict(sd, strict=True)
+    if use_real_ldm:
+        # the real LatentDiffusion wrapper (ddpm.py:434) around the same UNet: proves the stub's
+        # schedule/apply_model equal the reference's
+        with open(os.path.join(REF, "inference/config/Stage2_LDM.yaml")) as f:
+            y = yaml.safe_load(f)["model"]
+        from diff_foley.util import instantiate_from_config
+        y["params"]["unet_config"]["params"].update(
+            model_channels=cfg["model_channels"], channel_mult=list(cfg["channel_mult"]),
+            num_heads=cfg["num_heads"], context_dim=cfg["context_dim"],
+            attention_resolutions=list(cfg["attention_resolutions"]))
+        ldm = instantiate_from_config(y).eval()
+        ldm.model.diffusion_model.load_state_dict(sd, strict=True)
+        model = ldm
+    else:
+        model = _StubLDM(unet)
+    g = torch.Generator().manual_seed(seed + 2000)
+    x_T = torch.randn(n_clips, cfg["in_channels"], cfg["latent_h"], cfg["latent_w"], generator=g)
+    cond = torch.randn(n_clips, cfg["context_len"], cfg["context_dim"], generator=g)
+    uncond = torch.zeros_like(cond)
+    sampler = CpuDDIM(model)
+    with torch.no_grad():
+        samples, inter = sampler.sample(S=steps, batch_size=n_clips,
+                                        shape=(cfg["in_channels"], cfg["latent_h"], cfg["latent_w"]),
+                                        conditioning=cond, eta=0.0, verbose=False, x_T=x_T,
+                                        unconditional_guidance_scale=scale,
+                                        unconditional_conditioning=uncond)
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"), x_T=x_T.numpy(), cond=cond.numpy(), samples=samples.numpy(),
+        pred_x0=inter["pred_x0"][-1].numpy(), seed=np.int64(seed), steps=np.int64(steps),
+        scale=np.float32(scale), ddim_timesteps=np.asarray(sampler.ddim_timesteps),
+        ddim_alphas=np.asarray(sampler.ddim_alphas), ddim_alphas_prev=np.asarray(sampler.ddim_alphas_prev),
+        ddim_sqrt_one_minus_alphas=np.asarray(sampler.ddim_sqrt_one_minus_alphas),
+        ddim_sigmas=np.asarray(sampler.ddim_sigmas))
+    print(f"{name}: latent rms {float(samples.pow(2).mean().sqrt()):.4f} ({time.time() - t0:.1f}s)")
+
+
+SMALL = unet_oracle.small_unet_cfg()                       # 64 ch, heads 4 -> head dims 16/32/64
+SMALL_ODD = unet_oracle.small_unet_cfg(model_channels=128, channel_mult=(1, 2), num_heads=8,
+                                       context_dim=64, latent_h=8, latent_w=16, context_len=33,
+                                       attention_resolutions=(2, 1))  # head dims 16/32, ragged ctx
+FULL = unet_oracle.DIFF_FOLEY_UNET
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    torch.set_num_threads(os.cpu_count())
+    taps = ("input_blocks.1", "input_blocks.3", "input_blocks.4", "middle_block", "output_blocks.2",
+            "output_blocks.5", "output_blocks.11")
+    gen_unet("unet_small", SMALL, 1, 2, [961, 961], taps)
+    gen_unet("unet_small_b3", SMALL, 2, 3, [41, 500, 999])
+    gen_unet("unet_small_odd", SMALL_ODD, 3, 2, [1, 1], ("input_blocks.1", "middle_block"))
+    gen_ddim("ddim_small", SMALL, 1, 2, 25, 4.5)
+    gen_ddim("ddim_small_ldm", SMALL, 4, 1, 5, 4.5, use_real_ldm=True)
+    if which == "all":
+        gen_unet("unet_full", FULL, 7, 2, [961, 961])
+        gen_unet("unet_full_t41", FULL, 7, 2, [41, 41])
+        gen_ddim("ddim_full", FULL, 7, 1, 25, 4.5)

@@ -1,0 +1,102 @@
+"""CPU tests: the oracle (oracle/) against the golden vectors produced by the reference's own
+modules (tests/golden/make_golden.py).  These pin the oracle; the GPU tests then compare the CUDA
+path with the oracle and with the same golden files."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ddim_oracle, unet_oracle
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SMALL = unet_oracle.small_unet_cfg()
+SMALL_ODD = unet_oracle.small_unet_cfg(model_channels=128, channel_mult=(1, 2), num_heads=8,
+                                       context_dim=64, latent_h=8, latent_w=16, context_len=33,
+                                       attention_resolutions=(2, 1))
+FULL = unet_oracle.DIFF_FOLEY_UNET
+
+
+def load(name):
+    path = os.path.join(GOLD, name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{name}.npz not generated")
+    return np.load(path)
+
+
+def rel_l2(a, b):
+    a, b = torch.as_tensor(a).double().flatten(), torch.as_tensor(b).double().flatten()
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.mark.parametrize("name,cfg", [("unet_small", SMALL), ("unet_small_b3", SMALL),
+                                      ("unet_small_odd", SMALL_ODD)])
+def test_unet_oracle_matches_reference(name, cfg):
+    g = load(name)
+    sd = unet_oracle.seeded_state_dict(cfg, int(g["seed"]))
+    taps = {}
+    eps = unet_oracle.unet_forward(sd, cfg, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]),
+                                   torch.from_numpy(g["ctx"]), taps)
+    # same fp32 ATen kernels in a slightly different call order: agreement to a few ulp
+    assert rel_l2(eps, g["eps"]) < 2e-6
+    for k in g.files:
+        if k.startswith("tap:"):
+            assert rel_l2(taps[k[4:]], g[k]) < 2e-6, k
+
+
+def test_unet_oracle_full_size():
+    """The real Diff-Foley configuration (859.5 M parameters), one CFG step at t = 961."""
+    g = load("unet_full")
+    sd = unet_oracle.seeded_state_dict(FULL, int(g["seed"]))
+    assert sum(v.numel() for v in sd.values()) == 859_520_964
+    eps = unet_oracle.unet_forward(sd, FULL, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]),
+                                   torch.from_numpy(g["ctx"]))
+    assert rel_l2(eps, g["eps"]) < 5e-6
+
+
+def test_param_shapes_cover_reference_keys():
+    shapes = unet_oracle.unet_param_shapes(FULL)
+    assert len(shapes) == 686
+    assert shapes["input_blocks.0.0.weight"] == (320, 4, 3, 3)
+    assert shapes["output_blocks.0.0.skip_connection.weight"] == (1280, 2560, 1, 1)
+    assert shapes["middle_block.1.transformer_blocks.0.attn2.to_k.weight"] == (1280, 768)
+    assert shapes["output_blocks.5.2.conv.weight"] == (1280, 1280, 3, 3)
+    assert shapes["output_blocks.2.1.conv.weight"] == (1280, 1280, 3, 3)
+
+
+def test_schedule_matches_reference_sampler():
+    g = load("ddim_small")
+    c = ddim_oracle.ddim_coefficients(int(g["steps"]))
+    ts = np.asarray(g["ddim_timesteps"])
+    assert ts[0] == 1 and ts[-1] == 961 and len(ts) == 25
+    assert np.array_equal(c["timesteps"], ts[::-1])
+    # bit-exact fp32 scalars, in the reference's own order (ascending t) -> flip ours
+    assert np.array_equal(c["a_t"][::-1], g["ddim_alphas"].astype(np.float32))
+    assert np.array_equal(c["sqrt_one_minus_at"][::-1], g["ddim_sqrt_one_minus_alphas"].astype(np.float32))
+    # the reference takes torch.full(...fp32).sqrt() of these (ddim.py:272); torch's CPU sqrt, not numpy's
+    a_prev = torch.tensor(g["ddim_alphas_prev"], dtype=torch.float32)
+    assert np.array_equal(c["sqrt_a_prev"][::-1], a_prev.sqrt().numpy())
+    assert np.all(np.asarray(g["ddim_sigmas"]) == 0)
+
+
+@pytest.mark.parametrize("name", ["ddim_small", "ddim_small_ldm"])
+def test_ddim_oracle_matches_reference_sampler(name):
+    g = load(name)
+    sd = unet_oracle.seeded_state_dict(SMALL, int(g["seed"]))
+    cond = torch.from_numpy(g["cond"])
+    fn = lambda x, t, c: unet_oracle.unet_forward(sd, SMALL, x, t, c)
+    x, pred = ddim_oracle.ddim_sample(fn, torch.from_numpy(g["x_T"]), cond, torch.zeros_like(cond),
+                                      float(g["scale"]), int(g["steps"]))
+    assert rel_l2(x, g["samples"]) < 2e-5
+    assert rel_l2(pred, g["pred_x0"]) < 2e-5
+
+
+def test_ddim_step_linearity():
+    """size-independent property: the update is affine in (x, e) with the schedule's coefficients."""
+    c = ddim_oracle.ddim_coefficients(25)
+    g = torch.Generator().manual_seed(0)
+    x, eu, ec = (torch.randn(3, 4, 16, 64, generator=g) for _ in range(3))
+    xp, p0 = ddim_oracle.ddim_step(x, eu, ec, 4.5, c, 3)
+    e = eu + 4.5 * (ec - eu)
+    assert torch.allclose(p0 * float(c["sqrt_at"][3]) + float(c["sqrt_one_minus_at"][3]) * e, x, atol=1e-5)
+    assert torch.allclose(xp, float(c["sqrt_a_prev"][3]) * p0 + float(c["dir_coef"][3]) * e, atol=1e-6)

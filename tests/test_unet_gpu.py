@@ -1,0 +1,106 @@
+"""Whole-model parity on the GPU, through the same C ABI the drop-in module uses.
+
+Tolerances: the CUDA path rounds GEMM operands to fp16 (10-bit mantissa, the same operand precision
+as the TF32 convolutions the reference's own GPU path uses by default -- SURVEY 5 'Mixed
+precision') and accumulates in fp32, so single-forward eps agrees with the fp32 CPU reference to
+~1e-3 rel-L2.  The north-star target is <= 1e-3 on the decoded mel after 25 steps; the measured
+values are printed and recorded in DESIGN.md.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from diff_foley_b200.ldm import LatentDiffusionB200
+from diff_foley_b200.unet import UNetModelB200
+from oracle import unet_oracle
+from tests.test_host_cpu import unet_kwargs
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SMALL = unet_oracle.small_unet_cfg()
+SMALL_ODD = unet_oracle.small_unet_cfg(model_channels=128, channel_mult=(1, 2), num_heads=8,
+                                       context_dim=64, latent_h=8, latent_w=16, context_len=33,
+                                       attention_resolutions=(2, 1))
+FULL = unet_oracle.DIFF_FOLEY_UNET
+
+
+def rel_l2(a, b):
+    a, b = torch.as_tensor(a).double().flatten().cpu(), torch.as_tensor(b).double().flatten().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+_models = {}
+
+
+def model_for(cfg, seed):
+    key = (tuple(sorted((k, str(v)) for k, v in cfg.items())), seed)
+    if key not in _models:
+        m = UNetModelB200(**unet_kwargs(cfg))
+        m.load_state_dict(unet_oracle.seeded_state_dict(cfg, seed), strict=True)
+        _models[key] = m.cuda()
+    return _models[key]
+
+
+@pytest.mark.parametrize("name,cfg", [("unet_small", SMALL), ("unet_small_b3", SMALL),
+                                      ("unet_small_odd", SMALL_ODD), ("unet_full", FULL),
+                                      ("unet_full_t41", FULL)])
+def test_unet_forward_matches_reference_golden(name, cfg):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    m = model_for(cfg, int(g["seed"]))
+    x, t, ctx = (torch.from_numpy(g[k]).cuda() for k in ("x", "t", "ctx"))
+    eps = m(x, t, context=ctx)
+    torch.cuda.synchronize()
+    assert torch.isfinite(eps).all()
+    err = rel_l2(eps, g["eps"])
+    print(f"\n[parity] {name}: eps rel-L2 vs reference fp32 = {err:.3e}")
+    assert err < 3e-3
+    # determinism + launch count (no silent fallback: the engine really launched its plan)
+    eps2 = m(x, t, context=ctx)
+    assert torch.equal(eps, eps2)
+    assert m.last_launch_count() > 100
+
+
+def test_unet_float_timesteps_and_cached_context():
+    """DPM-Solver feeds fractional fp32 t (dpm_solver.py:1296-1305); the t-emb kernel accepts both."""
+    g = np.load(os.path.join(GOLD, "unet_small.npz"))
+    m = model_for(SMALL, int(g["seed"]))
+    x, t, ctx = (torch.from_numpy(g[k]).cuda() for k in ("x", "t", "ctx"))
+    a = m(x, t, context=ctx)
+    b = m(x, t.float(), context=ctx)
+    assert torch.equal(a, b)
+    sd = unet_oracle.seeded_state_dict(SMALL, int(g["seed"]))
+    tf = torch.tensor([333.25, 12.5])
+    ref = unet_oracle.unet_forward(sd, SMALL, x.cpu(), tf, ctx.cpu())
+    out = m(x, tf.cuda(), context=ctx)
+    assert rel_l2(out, ref) < 3e-3
+
+
+@pytest.mark.parametrize("name,cfg", [("ddim_small", SMALL), ("ddim_full", FULL)])
+def test_fused_ddim_matches_reference_sampler(name, cfg):
+    """DDIM-25, CFG 4.5 (BASELINE config 2 for 'ddim_full'): one dfb_ddim_sample call vs the latent the
+    reference's DDIMSampler.sample produced on CPU fp32 from the same x_T / weights / conditioning."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    unet = model_for(cfg, int(g["seed"]))
+    ldm = LatentDiffusionB200(unet, cond_stage_params=dict(origin_dim=64, embed_dim=cfg["context_dim"], seq_len=40)).cuda()
+    cond = torch.from_numpy(g["cond"]).cuda()
+    x_T = torch.from_numpy(g["x_T"]).cuda()
+    n = x_T.shape[0]
+    samples, inter = ldm.sample_log_diff_sampler(cond, n, "DDIM", int(g["steps"]), size_len=cfg["latent_w"],
+                                                 unconditional_guidance_scale=float(g["scale"]),
+                                                 unconditional_conditioning=torch.zeros_like(cond), x_T=x_T)
+    torch.cuda.synchronize()
+    assert torch.isfinite(samples).all()
+    err = rel_l2(samples, g["samples"])
+    err0 = rel_l2(inter["pred_x0"][-1], g["pred_x0"])
+    print(f"\n[parity] {name}: latent after {int(g['steps'])} steps rel-L2 = {err:.3e}, pred_x0 = {err0:.3e}")
+    assert err < 2e-2
+    # the host-loop path (apply_model + dfb_ddim_step) must agree with the fused graph path bit-for-bit
+    samples2, _ = ldm.sample_log_diff_sampler(cond, n, "DDIM", int(g["steps"]), size_len=cfg["latent_w"],
+                                              unconditional_guidance_scale=float(g["scale"]),
+                                              unconditional_conditioning=torch.zeros_like(cond), x_T=x_T,
+                                              callback=lambda i: None)
+    torch.cuda.synchronize()
+    print(f"[parity] {name}: fused vs host-loop rel-L2 = {rel_l2(samples2, samples):.3e}")
+    assert rel_l2(samples2, samples) < 1e-5
