@@ -48,6 +48,8 @@ SIGNATURES = {
     "dfb_unet_forward": (_i, [_vp, _fp, _i, _vp, _i, _fp, _i, _fp, _i, _vp]),
     "dfb_ddim_sample": (_i, [_vp, _fp, _fp, _fp, _i, _i, _f, _i, _i64p, C.POINTER(_f), C.POINTER(_f),
                              C.POINTER(_f), C.POINTER(_f), _fp, _vp]),
+    "dfb_unet_debug_num_taps": (_i, [_vp, _i]),
+    "dfb_unet_debug_tap": (_i, [_vp, _i, _i, C.c_char_p, _i, C.POINTER(C.c_int32), _fp, _vp]),
     "dfb_unet_last_launch_count": (C.c_longlong, [_vp]),
     "dfb_unet_destroy": (_i, [_vp]),
     "dfb_gemm": (_i, [_vp, _vp, _i, _i, _i, _fp, _fp, _i, _fp, _vp, _i, _vp]),

@@ -17,6 +17,7 @@ const char* last_error();
   do {                                                                                      \
     cudaError_t _e = (expr);                                                                \
     if (_e != cudaSuccess) {                                                                \
+      (void)cudaGetLastError(); /* clear the non-sticky error state */                       \
       ::dfb::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + \
                        __FILE__ + ":" + std::to_string(__LINE__));                          \
       return -2;                                                                            \

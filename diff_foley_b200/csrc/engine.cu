@@ -118,6 +118,8 @@ struct Plan {
   int b_eff = 0;
   std::vector<std::function<int(cudaStream_t)>> ops;
   std::vector<void*> owned;  // device allocations of this plan
+  struct Tap { std::string name; const float* p; int H, W, C; };
+  std::vector<Tap> taps;     // block outputs (valid after a forward only for buffers not yet reused)
 };
 
 }  // namespace dfb
@@ -184,6 +186,7 @@ struct dfb_unet {
     float* x_ptr = nullptr;
     float* px0_ptr = nullptr;
     cudaGraphExec_t exec = nullptr;
+    cudaStream_t cap_stream = nullptr;
     int cap_S = 0;
   } smp;
 
@@ -523,6 +526,13 @@ struct Builder {
     if (rc) return;
     if (ep.bias == nullptr && ep.act != ACT_GEGLU) ep.bias = lin.b;
     if (ep.act == ACT_GEGLU) ep.bias = lin.b;
+    {
+      // every GEMM output lands in one of the shared scratch / stream buffers: size them for it
+      const size_t rows = (size_t)g.B * g.T * g.H * g.W;
+      if (ep.out_f32) use32(rows * ep.ldo);
+      if (ep.out_f16) use16(rows * ep.ldo);
+      use16(rows * g.C);
+    }
     IGemmPlan ip;
     if (dry) {
       // plan with dummy (aligned, non-null) pointers just to learn tiling / workspace needs
@@ -705,7 +715,18 @@ static int build_plan(dfb_unet* e, int B, Plan** out) {
     float* hbuf[3] = {nullptr, nullptr, nullptr};
     __half *t16a = nullptr, *t16b = nullptr;
     float* emb_all = nullptr;
-    if (!b.dry) {
+    if (b.dry) {
+      // the measuring pass never launches: give every buffer a distinct non-null fake address so
+      // the planners' pointer validation passes
+      for (int i = 0; i < 3; ++i) {
+        b.a16[i] = reinterpret_cast<__half*>((uintptr_t)0x10000 * (i + 1));
+        b.t32[i] = reinterpret_cast<float*>((uintptr_t)0x10000 * (i + 4));
+        hbuf[i] = reinterpret_cast<float*>((uintptr_t)0x10000 * (i + 7));
+      }
+      t16a = reinterpret_cast<__half*>((uintptr_t)0x10000 * 10);
+      t16b = reinterpret_cast<__half*>((uintptr_t)0x10000 * 11);
+      emb_all = reinterpret_cast<float*>((uintptr_t)0x10000 * 12);
+    } else {
       for (int i = 0; i < 3; ++i) {
         b.a16[i] = (__half*)palloc(s_need16 * sizeof(__half));
         b.t32[i] = (float*)palloc(s_need32 * sizeof(float));
@@ -733,12 +754,17 @@ static int build_plan(dfb_unet* e, int B, Plan** out) {
     auto new_skip = [&](int C, int h, int w) -> float* {
       const size_t n = (size_t)B * h * w * C;
       b.use32(n);
-      if (b.dry) { skips.push_back(nullptr); return nullptr; }
+      if (b.dry) {
+        float* fake = reinterpret_cast<float*>((uintptr_t)0x10000 * (20 + skips.size()));
+        skips.push_back(fake);
+        return fake;
+      }
       float* p = (float*)palloc(n * sizeof(float));
       skips.push_back(p);
       return p;
     };
     float* h = new_skip(mc, H, W);
+    if (!b.dry) plan->taps.push_back({"input_blocks.0", h, H, W, mc});
     {
       dfb_unet* eng = e;
       const int Bc = B, Cin = c.in_channels, Hc = H, Wc = W;
@@ -748,10 +774,12 @@ static int build_plan(dfb_unet* e, int B, Plan** out) {
       });
     }
     int hrot = 0;
+    const char* dbg = getenv("DFB_DEBUG_TAPS");
+    const bool keep_all = dbg && dbg[0] == '1';
     auto next_h = [&](const float* avoid0, const float* avoid1) -> float* {
+      if (keep_all && !b.dry) return (float*)palloc(s_need32 * sizeof(float));
       for (int k = 0; k < 3; ++k) {
         float* cand = hbuf[(hrot + k) % 3];
-        if (b.dry) return nullptr;
         if (cand != avoid0 && cand != avoid1) { hrot = (hrot + k + 1) % 3; return cand; }
       }
       return nullptr;
@@ -781,6 +809,7 @@ static int build_plan(dfb_unet* e, int B, Plan** out) {
         }
       }
       h = const_cast<float*>(cur);
+      if (!b.dry) plan->taps.push_back({"input_blocks." + std::to_string(bi), cur, H, W, e->in_block_ch[bi]});
     }
     // ---- middle block
     const float* cur = h;
@@ -794,8 +823,9 @@ static int build_plan(dfb_unet* e, int B, Plan** out) {
       }
       cur = o;
     }
-    // ---- output blocks (skip concat handled inside GroupNorm / raw-copy)
     int cur_ch = e->res[e->mid_block.back().idx].cout;
+    if (!b.dry) plan->taps.push_back({"middle_block", cur, H, W, cur_ch});
+    // ---- output blocks (skip concat handled inside GroupNorm / raw-copy)
     for (size_t bi = 0; bi < e->out_blocks.size(); ++bi) {
       const BlockDesc& bd = e->out_blocks[bi];
       const float* skip = skips.back();
@@ -815,6 +845,7 @@ static int build_plan(dfb_unet* e, int B, Plan** out) {
         }
         cur = o;
       }
+      if (!b.dry) plan->taps.push_back({"output_blocks." + std::to_string(bi), cur, H, W, cur_ch});
     }
     // ---- head: GN + SiLU + conv3x3 -> NCHW (openai_unetmodel.py:682-686, 742)
     {
@@ -1106,10 +1137,14 @@ int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* unco
   }
   if (sm.exec == nullptr || sm.x_ptr != x || sm.px0_ptr != pred_x0) {
     if (sm.exec) { cudaGraphExecDestroy(sm.exec); sm.exec = nullptr; }
+    // the caller's stream may be the legacy default stream, which cannot capture: record the step
+    // on an engine-owned stream, replay the instantiated graph on the caller's stream
+    if (sm.cap_stream == nullptr)
+      DFB_CUDA_OK(cudaStreamCreateWithFlags(&sm.cap_stream, cudaStreamNonBlocking));
     cudaGraph_t graph = nullptr;
-    DFB_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    r = one_step(s);
-    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    DFB_CUDA_OK(cudaStreamBeginCapture(sm.cap_stream, cudaStreamCaptureModeThreadLocal));
+    r = one_step(sm.cap_stream);
+    cudaError_t ce = cudaStreamEndCapture(sm.cap_stream, &graph);
     if (r) { if (graph) cudaGraphDestroy(graph); return r; }
     if (ce != cudaSuccess) { set_error(std::string("graph capture failed: ") + cudaGetErrorString(ce)); return DFB_E_CUDA; }
     ce = cudaGraphInstantiate(&sm.exec, graph, 0);
@@ -1126,6 +1161,38 @@ int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* unco
   return 0;
 }
 
+int dfb_unet_debug_num_taps(dfb_handle h, int b_eff) {
+  if (!h) return 0;
+  auto it = h->plans.find(b_eff);
+  return it == h->plans.end() ? 0 : (int)it->second->taps.size();
+}
+int dfb_unet_debug_tap(dfb_handle h, int b_eff, int i, char* name, int name_cap, int32_t* hwc,
+                       float* dst_dev, void* stream) {
+  if (!h) { set_error("null handle"); return DFB_E_INVALID; }
+  auto it = h->plans.find(b_eff);
+  if (it == h->plans.end() || i < 0 || i >= (int)it->second->taps.size()) {
+    set_error("debug_tap: no such plan / tap");
+    return DFB_E_INVALID;
+  }
+  const Plan::Tap& t = it->second->taps[i];
+  if (name && name_cap > 0) { strncpy(name, t.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (hwc) { hwc[0] = t.H; hwc[1] = t.W; hwc[2] = t.C; }
+  if (dst_dev) {
+    cudaError_t ce = cudaMemcpyAsync(dst_dev, t.p, (size_t)b_eff * t.H * t.W * t.C * sizeof(float),
+                                     cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    if (ce != cudaSuccess) {
+      (void)cudaGetLastError();
+      char buf[256];
+      snprintf(buf, sizeof(buf), "debug_tap %s: memcpy %p <- %p (%d x %d x %d x %d) failed: %s",
+               t.name.c_str(), (void*)dst_dev, (const void*)t.p, b_eff, t.H, t.W, t.C,
+               cudaGetErrorString(ce));
+      set_error(buf);
+      return DFB_E_CUDA;
+    }
+  }
+  return 0;
+}
+
 long long dfb_unet_last_launch_count(dfb_handle h) { return h ? h->last_launches : 0; }
 
 int dfb_unet_destroy(dfb_handle h) {
@@ -1133,6 +1200,7 @@ int dfb_unet_destroy(dfb_handle h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   if (h->smp.exec) cudaGraphExecDestroy(h->smp.exec);
+  if (h->smp.cap_stream) cudaStreamDestroy(h->smp.cap_stream);
   for (auto& kv : h->plans)
     for (void* p : kv.second->owned) cudaFree(p);
   for (void* p : h->owned) cudaFree(p);

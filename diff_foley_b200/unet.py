@@ -274,5 +274,19 @@ class UNetModelB200(nn.Module):
                     "dfb_unet_forward")
         return out.to(x.dtype)
 
+    def debug_taps(self, b_eff):
+        """Block outputs of the last forward at this batch size as {name: NCHW tensor} (test aid)."""
+        lib, out = L.lib(), {}
+        for i in range(lib.dfb_unet_debug_num_taps(self._handle, b_eff)):
+            name = C.create_string_buffer(64)
+            hwc = (C.c_int32 * 3)()
+            L.check(lib.dfb_unet_debug_tap(self._handle, b_eff, i, name, 64, hwc, None, None), "debug_tap")
+            t = torch.empty(b_eff, hwc[0], hwc[1], hwc[2], device=f"cuda:{self._device_index}")
+            L.check(lib.dfb_unet_debug_tap(self._handle, b_eff, i, name, 64, hwc, L.ptr(t), L.cur_stream()),
+                    "debug_tap")
+            out[name.value.decode()] = t.permute(0, 3, 1, 2).contiguous()
+        torch.cuda.synchronize()
+        return out
+
     def last_launch_count(self):
         return int(L.lib().dfb_unet_last_launch_count(self._handle)) if self._handle else 0

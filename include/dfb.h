@@ -85,6 +85,13 @@ int dfb_ddim_sample(dfb_handle h, float* x_dev, const float* cond_dev, const flo
                     int n_clips, int ctx_len, float cfg_scale, int n_steps, const int64_t* timesteps,
                     const float* sqrt_one_minus_at, const float* sqrt_at, const float* sqrt_a_prev,
                     const float* dir_coef, float* pred_x0_dev, void* stream);
+/* Debug/test aid: block outputs ("input_blocks.3", "middle_block", ...) of the plan for b_eff,
+ * channels-last fp32 [b_eff, H, W, C].  With the environment variable DFB_DEBUG_TAPS=1 set before the
+ * first forward every block output keeps its own buffer; otherwise only the skip-stack tensors
+ * (input blocks) are still intact after a forward. */
+int dfb_unet_debug_num_taps(dfb_handle h, int b_eff);
+int dfb_unet_debug_tap(dfb_handle h, int b_eff, int i, char* name, int name_cap, int32_t* hwc,
+                       float* dst_dev, void* stream);
 /* kernels launched by the most recent forward / sample call (for bench.py's gpu_launches) */
 long long dfb_unet_last_launch_count(dfb_handle h);
 int dfb_unet_destroy(dfb_handle h);

@@ -11,17 +11,9 @@ from diff_foley_b200 import _lib as L
 from diff_foley_b200.ddim import DDIMSamplerB200, make_ddim_timesteps
 from diff_foley_b200.unet import UNetModelB200
 from oracle import ddim_oracle, unet_oracle
+from helpers import unet_kwargs
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-
-
-def unet_kwargs(cfg):
-    return dict(image_size=32, in_channels=cfg["in_channels"], out_channels=cfg["out_channels"],
-                model_channels=cfg["model_channels"], attention_resolutions=list(cfg["attention_resolutions"]),
-                num_res_blocks=cfg["num_res_blocks"], channel_mult=list(cfg["channel_mult"]),
-                num_heads=cfg["num_heads"], use_spatial_transformer=True, transformer_depth=1,
-                context_dim=cfg["context_dim"], use_checkpoint=True, legacy=False,
-                latent_size=(cfg["latent_h"], cfg["latent_w"]), max_context_len=40)
 
 
 def test_library_exports_every_declared_symbol():

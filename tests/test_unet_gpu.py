@@ -15,7 +15,7 @@ import torch
 from diff_foley_b200.ldm import LatentDiffusionB200
 from diff_foley_b200.unet import UNetModelB200
 from oracle import unet_oracle
-from tests.test_host_cpu import unet_kwargs
+from helpers import unet_kwargs
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
