@@ -1,0 +1,312 @@
+"""bench.py -- headline benchmark: mel-latents/sec for DDIM-25 with classifier-free guidance 4.5
+(BASELINE.json metric) on the Diff-Foley UNet (859.5 M parameters, latent [4,16,64], 32x768 context).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--clips-per-gpu C] [--impl ours|reference]
+
+A "step" is one full 25-step DDIM sampling of the rank's clips (one pass of the hot path over one
+batch).  N = 1 is BASELINE config 2 (B = 1 clip, B_eff = 2 under CFG).  For N > 1 (torchrun, one
+process per GPU, NCCL) the (clip, guidance-branch) units of N*C clips are sharded over the ranks and
+joined by a per-step NCCL all-gather of eps (BASELINE config 4's scheme), per-GPU work fixed => weak
+scaling.  Prints ONE JSON line on rank 0.
+
+`--impl reference` times the reference algorithm's CPU path (the oracle port: the reference is pure
+Python/PyTorch, nothing to compile) on the host cores: each step is ONE DDIM step (UNet forward at
+B_eff = 2 + update) of the same workload, a bounded sample, reported in the same unit.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mel-latents/sec (DDIM-25, CFG=4.5)"
+UNIT = "latents/s"
+DDIM_STEPS = 25
+CFG_SCALE = 4.5
+UNET_GFLOP_PER_SAMPLE = 177.861  # SURVEY 6 / BASELINE.md 2: 2*MAC over conv/linear/attention core
+FULL = dict(image_size=32, in_channels=4, out_channels=4, model_channels=320,
+            attention_resolutions=[4, 2, 1], num_res_blocks=2, channel_mult=[1, 2, 4, 4], num_heads=8,
+            use_spatial_transformer=True, transformer_depth=1, context_dim=768, use_checkpoint=True,
+            legacy=False)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]),
+                    tf_sust=float(p["bf16_tflops_sustained"]), src="measured (MEASURED_PEAKS.json)")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def cpu_reference_step_seconds(steps, warmup, state_dict=None):
+    """Times the oracle port of the reference's CPU path: one p_sample_ddim with CFG for B = 1
+    (UNet forward at B_eff = 2, fp32, all host threads) per step.  Returns (mean seconds, cores)."""
+    import torch
+    from oracle import ddim_oracle, unet_oracle  # cpu_baseline / reference leg: allowed to use the oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = unet_oracle.DIFF_FOLEY_UNET
+    sd = state_dict if state_dict is not None else unet_oracle.seeded_state_dict(cfg, 7)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(1, 4, 16, 64, generator=g)
+    f = torch.nn.functional.normalize(torch.randn(1, 32, 512, generator=g), dim=-1)
+    cond = torch.randn(1, 32, 768, generator=g) * 0.5 + f.mean() * 0  # embedded context stand-in
+    unc = torch.zeros_like(cond)
+    c = ddim_oracle.ddim_coefficients(DDIM_STEPS)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        ts = torch.full((2,), int(c["timesteps"][i % DDIM_STEPS]), dtype=torch.long)
+        e = unet_oracle.unet_forward(sd, cfg, torch.cat([x, x]), ts, torch.cat([unc, cond]))
+        x, _ = ddim_oracle.ddim_step(x, e[:1], e[1:], CFG_SCALE, c, i % DDIM_STEPS)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times), cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 40)), max(1, min(args.warmup, 3))
+    sec, cores = cpu_reference_step_seconds(steps, warmup)
+    value = 1.0 / (DDIM_STEPS * sec)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3 * DDIM_STEPS, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config 2: DDIM-25, CFG 4.5, B=1 clip (B_eff=2), UNet 859.5M, latent 4x16x64, ctx 32x768",
+                   "timed": "each step = 1 of the 25 DDIM steps (UNet fwd at B_eff=2 + update); value = 1/(25*step_s)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{steps} single DDIM steps (UNet fwd B_eff=2 + update), fp32 torch CPU, {cores} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from diff_foley_b200.ldm import LatentDiffusionB200
+    from diff_foley_b200.parallel import sharded_ddim_sample
+    from diff_foley_b200.unet import UNetModelB200
+    from diff_foley_b200.weights import randomize_parameters_
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    C = args.clips_per_gpu
+    B_global = C * world
+
+    unet = UNetModelB200(**FULL, max_batch=max(2 * C, 2), max_context_len=40).to(dev)
+    randomize_parameters_(unet, seed=7)
+    ldm = LatentDiffusionB200(unet).to(dev)
+    randomize_parameters_(ldm.cond_stage_model, seed=8)
+    unet.engine(dev)
+
+    g = torch.Generator().manual_seed(1234)
+    x_T_host = torch.randn(B_global, 4, 16, 64, generator=g).pin_memory()
+    feats_host = torch.nn.functional.normalize(torch.randn(B_global, 32, 512, generator=g), dim=-1).pin_memory()
+    out_host = torch.empty(B_global, 4, 16, 64).pin_memory()
+    x_T = x_T_host.to(dev)
+    cond = ldm.get_learned_conditioning(feats_host.to(dev))
+    unc = torch.zeros_like(cond)
+
+    def sample_resident():
+        if world == 1:
+            s, _ = ldm.sample_log_diff_sampler(cond, B_global, "DDIM", DDIM_STEPS, unconditional_guidance_scale=CFG_SCALE,
+                                               unconditional_conditioning=unc, x_T=x_T)
+            return s
+        return sharded_ddim_sample(ldm, x_T, cond, unc, CFG_SCALE, DDIM_STEPS)
+
+    def sample_e2e():
+        f = feats_host.to(dev, non_blocking=True)
+        xt = x_T_host.to(dev, non_blocking=True)
+        c = ldm.get_learned_conditioning(f)
+        u = torch.zeros_like(c)
+        if world == 1:
+            s, _ = ldm.sample_log_diff_sampler(c, B_global, "DDIM", DDIM_STEPS, unconditional_guidance_scale=CFG_SCALE,
+                                               unconditional_conditioning=u, x_T=xt)
+        else:
+            s = sharded_ddim_sample(ldm, xt, c, u, CFG_SCALE, DDIM_STEPS)
+        out_host.copy_(s, non_blocking=True)
+        return s
+
+    def timed(fn, k, w):
+        for _ in range(w):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    K, W = max(1, args.steps), max(3, args.warmup)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_total = timed(sample_resident, K, W)
+    launches = unet.last_launch_count()
+    clk = clocks.stop() if rank == 0 else None
+    ms_e2e = timed(sample_e2e, K, 1)
+    value = B_global * K / (ms_total / 1e3)
+    e2e_value = B_global * K / (ms_e2e / 1e3)
+
+    line = None
+    if rank == 0:
+        pk = peaks()
+        # ---- live roofline of the dominant kernel (the tcgen05 implicit GEMM), event-timed per launch
+        prof = unet.profile(torch.cat([x_T[:C], x_T[:C]]), torch.full((2 * C,), 961, device=dev, dtype=torch.long),
+                            torch.cat([unc[:C], cond[:C]]), iters=5)
+        ig = [p for p in prof if p["kind"].startswith("igemm")]
+        ig_ms = sum(p["ms"] for p in ig)
+        all_ms = sum(p["ms"] for p in prof)
+        w_bytes = sum(2.0 * p["N"] * p["K"] for p in ig)       # fp16 weights, streamed once per forward
+        ig_bytes = sum(p["bytes"] for p in ig)
+        ig_flops = sum(p["flops"] for p in ig)
+        by_kind = {}
+        for p in prof:
+            d = by_kind.setdefault(p["kind"], [0, 0.0])
+            d[0] += 1; d[1] += p["ms"]
+        ach_gbs = ig_bytes / (ig_ms / 1e3) / 1e9
+        ach_tf = ig_flops / (ig_ms / 1e3) / 1e12
+        hbm_bound = (ig_bytes / pk["hbm"] / 1e9) >= (ig_flops / pk["tf_sust"] / 1e12)
+        roofline = {
+            "kernel": "igemm_tcgen05_kernel (all Linear / 1x1 / 3x3 conv launches of one UNet forward)",
+            "bound": "hbm" if hbm_bound else "tensor",
+            "achieved": ach_gbs if hbm_bound else ach_tf,
+            "peak": pk["hbm"] if hbm_bound else pk["tf_sust"],
+            "unit": "GB/s" if hbm_bound else "TFLOP/s",
+            "frac": (ach_gbs / pk["hbm"]) if hbm_bound else (ach_tf / pk["tf_sust"]),
+            "traffic": None, "peak_source": pk["src"],
+            "launches_per_forward": len(ig), "kernel_ms_per_forward": ig_ms, "all_kernels_ms_per_forward": all_ms,
+            "share_of_step": ig_ms / all_ms if all_ms else None,
+            "algorithmic_bytes_per_forward": ig_bytes, "weight_bytes_per_forward": w_bytes,
+            "algorithmic_flops_per_forward": ig_flops,
+            "achieved_tflops": ach_tf, "achieved_gbs": ach_gbs,
+            "by_kind_ms": {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in sorted(by_kind.items())},
+        }
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            sd = {k: v.detach().cpu() for k, v in unet.state_dict().items()}
+            sec, cores = cpu_reference_step_seconds(2, 1, sd)
+            cpu_baseline = {"value": 1.0 / (DDIM_STEPS * sec), "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"2 single DDIM steps (UNet fwd B_eff=2 + update) of the same workload, "
+                                      f"fp32 torch CPU oracle, {cores} threads; value = 1/(25*step_s)"}
+        lat_bytes = 4 * 16 * 64 * 4
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands, f32 accumulate + f32 residual stream", "data": "synthetic",
+            "config": {
+                "workload": ("config 2: DDIM-25, CFG 4.5, B=1 clip (B_eff=2), single B200" if world == 1 and C == 1 else
+                             f"config 4 scheme: DDIM-25, CFG 4.5, {B_global} clips, (clip,branch) units sharded over "
+                             f"{world} GPUs, per-step NCCL eps all-gather, {C} clips/GPU"),
+                "unet": "859.5M params, latent 4x16x64, context 32x768, random-init weights (zero_modules re-randomised)",
+                "clips_per_gpu": C, "global_clips": B_global, "ddim_steps": DDIM_STEPS, "cfg_scale": CFG_SCALE,
+                "unet_step_ms": ms_total / K / DDIM_STEPS,
+                "l2": "no explicit flush: each UNet pass streams 1.72 GB of fp16 weights (> 126 MB L2)",
+                "step_flops": 2 * C * UNET_GFLOP_PER_SAMPLE * 1e9 * DDIM_STEPS,
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
+                    "h2d_bytes_per_step": B_global * (32 * 512 * 4 + lat_bytes), "d2h_bytes_per_step": B_global * lat_bytes,
+                    "api": "LatentDiffusionB200.get_learned_conditioning + sample_log_diff_sampler('DDIM') from pinned host tensors"},
+            "gpu_launches": int(launches) * K,
+            "clocks": clk, "roofline": roofline,
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--clips-per-gpu", type=int, default=1)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

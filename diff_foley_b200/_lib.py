@@ -32,6 +32,12 @@ class UnetCfg(C.Structure):
     ]
 
 
+class OpInfo(C.Structure):
+    _fields_ = [("kind", C.c_char * 24), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+                ("splits", C.c_int32), ("ctas", C.c_int32), ("flops", C.c_double), ("bytes", C.c_double),
+                ("ms", C.c_float)]
+
+
 _vp, _i, _f, _fp, _sz = C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_size_t
 _i64p = C.POINTER(C.c_int64)
 
@@ -48,6 +54,7 @@ SIGNATURES = {
     "dfb_unet_forward": (_i, [_vp, _fp, _i, _vp, _i, _fp, _i, _fp, _i, _vp]),
     "dfb_ddim_sample": (_i, [_vp, _fp, _fp, _fp, _i, _i, _f, _i, _i64p, C.POINTER(_f), C.POINTER(_f),
                              C.POINTER(_f), C.POINTER(_f), _fp, _vp]),
+    "dfb_unet_profile": (_i, [_vp, _fp, _i, _vp, _i, _fp, _i, _i, C.POINTER(OpInfo), _i, C.POINTER(_i), _vp]),
     "dfb_unet_debug_num_taps": (_i, [_vp, _i]),
     "dfb_unet_debug_tap": (_i, [_vp, _i, _i, C.c_char_p, _i, C.POINTER(C.c_int32), _fp, _vp]),
     "dfb_unet_last_launch_count": (C.c_longlong, [_vp]),

@@ -142,6 +142,8 @@ int attention_launch(const __half* q, int ldq, const __half* k, int ldk, const _
   const size_t smem = (size_t)(ATT_KB * (d + 2) + ATT_KB * d + ATT_QB * d) * sizeof(__half) +
                       8 * ATT_KB * sizeof(float);
   dim3 grid((Lq + ATT_QB - 1) / ATT_QB, B * heads);
+  note("attention", 4.0 * B * heads * (double)Lq * Lk * d,
+       2.0 * B * heads * ((double)Lq * d * 2 + (double)Lk * d * 2), Lq, Lk, d, 1, grid.x * grid.y);
   attention_kernel<<<grid, ATT_THREADS, smem, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, heads, Lq,
                                                         Lk, d, dpad, scale);
   DFB_CUDA_OK(cudaGetLastError());

@@ -24,6 +24,20 @@ const char* last_error();
     }                                                                                       \
   } while (0)
 
+// Every launcher records what it just enqueued (kind + algorithmic flops / bytes) so the profiler
+// entry point (dfb_unet_profile) can attribute event-timed durations without a second op table.
+struct LaunchNote {
+  const char* kind;
+  double flops, bytes;
+  int M, N, K, splits, ctas;
+};
+extern thread_local LaunchNote g_note;
+inline void note(const char* kind, double flops, double bytes, int M = 0, int N = 0, int K = 0,
+                 int splits = 1, int ctas = 0) {
+  g_note.kind = kind; g_note.flops = flops; g_note.bytes = bytes;
+  g_note.M = M; g_note.N = N; g_note.K = K; g_note.splits = splits; g_note.ctas = ctas;
+}
+
 // one-time per-process kernel attribute setup (dynamic shared memory opt-in); idempotent
 int kernels_init();
 int igemm_init();

@@ -26,6 +26,7 @@ __global__ void temb_kernel(const void* __restrict__ t, int t_is_float, int B, i
 
 int temb_launch(const void* t, int t_is_float, int B, int dim, __half* out, cudaStream_t stream) {
   const int n = B * (dim / 2);
+  note("temb", 0.0, (double)B * dim * 2.0);
   temb_kernel<<<(n + 255) / 256, 256, 0, stream>>>(t, t_is_float, B, dim, out);
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
@@ -52,6 +53,7 @@ int cast_f16_launch(const float* src, __half* dst, size_t n, cudaStream_t stream
   }
   const size_t n4 = n / 4;
   const int blocks = (int)std::min<size_t>((n4 + 255) / 256, 148 * 8);
+  note("cast_f16", 0.0, (double)n * 6.0);
   cast_f16_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(src),
                                               reinterpret_cast<uint2*>(dst), n4);
   DFB_CUDA_OK(cudaGetLastError());
@@ -88,6 +90,7 @@ int upsample2x_f16_launch(const float* src, __half* dst, int B, int H, int W, in
   }
   const size_t total = (size_t)B * 4 * H * W * (C / 4);
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
+  note("upsample2x", 0.0, (double)total * 4 * (2.0 + 1.0));
   upsample2x_f16_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(src),
                                                     reinterpret_cast<uint2*>(dst), B, H, W, C / 4);
   DFB_CUDA_OK(cudaGetLastError());
@@ -127,6 +130,7 @@ int im2col_s2_launch(const float* src, __half* dst, int B, int H, int W, int C, 
   }
   const size_t total = (size_t)B * (H / 2) * (W / 2) * 9 * (C / 4);
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
+  note("im2col_s2", 0.0, (double)total * 4 * (2.0 + 1.0));
   im2col_s2_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(src),
                                                reinterpret_cast<uint2*>(dst), B, H, W, C / 4);
   DFB_CUDA_OK(cudaGetLastError());
@@ -160,6 +164,7 @@ __global__ void stem_conv_kernel(const float* __restrict__ x, int Bsrc, int Cin,
 
 int stem_conv_launch(const float* x, int Bsrc, int B, int Cin, int H, int W, const float* w,
                      const float* bias, int Cout, float* out, cudaStream_t stream) {
+  note("stem_conv", 2.0 * B * H * W * Cin * 9 * Cout, (double)B * H * W * Cout * 4.0);
   stem_conv_kernel<<<B * H * W, 128, Cin * 9 * sizeof(float), stream>>>(x, Bsrc, Cin, H, W, w, bias,
                                                                         Cout, out);
   DFB_CUDA_OK(cudaGetLastError());
@@ -210,6 +215,7 @@ int head_conv_launch(const __half* a, int B, int H, int W, int C, const float* w
     set_error("head_conv: Cout must be <= 4 and C even");
     return -1;
   }
+  note("head_conv", 2.0 * B * H * W * C * 9 * Cout, (double)B * H * W * C * 2.0);
   head_conv_kernel<<<(B * H * W + 7) / 8, 256, 0, stream>>>(a, B, H, W, C, w, bias, Cout, out);
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
@@ -245,6 +251,7 @@ int ddim_update_launch(const float* x, const float* eps_uncond, const float* eps
                        const float* grad, float cfg_scale, float sqrt_one_minus_at, float sqrt_at,
                        float sqrt_a_prev, float dir_coef, float grad_coef, float* x_prev,
                        float* pred_x0, size_t n, cudaStream_t stream) {
+  note("ddim_update", 0.0, (double)n * 20.0);
   ddim_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
       x, eps_uncond, eps_cond, grad, cfg_scale, sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef,
       grad_coef, x_prev, pred_x0, n);

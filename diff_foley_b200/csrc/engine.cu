@@ -26,6 +26,7 @@
 
 namespace dfb {
 
+thread_local LaunchNote g_note = {"none", 0, 0, 0, 0, 0, 1, 0};
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 const char* last_error() { return g_err.c_str(); }
@@ -1158,6 +1159,50 @@ int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* unco
     DFB_CUDA_OK(cudaGraphLaunch(sm.exec, s));
     h->last_launches += per_step;
   }
+  return 0;
+}
+
+int dfb_unet_profile(dfb_handle h, const float* x, int x_repeat, const void* t, int t_is_float,
+                     float* out, int b_eff, int iters, dfb_op_info* infos, int cap, int* n_ops,
+                     void* stream) {
+  if (!h || !x || !t || !out || !infos || !n_ops || iters < 1) { set_error("null argument"); return DFB_E_INVALID; }
+  if (!h->finalized) { set_error("profile before finalize"); return DFB_E_STATE; }
+  if (h->kv_b != b_eff) { set_error("profile: call dfb_unet_set_context for this batch size first"); return DFB_E_STATE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  Plan* p = nullptr;
+  int r = build_plan(h, b_eff, &p);
+  if (r) return r;
+  const int n = (int)p->ops.size();
+  *n_ops = n;
+  if (cap < n) { set_error("profile: info array too small, need " + std::to_string(n)); return DFB_E_INVALID; }
+  h->cur_x = x; h->cur_x_repeat = x_repeat; h->cur_t = t; h->cur_t_is_float = t_is_float; h->cur_out = out;
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) DFB_CUDA_OK(cudaEventCreate(&e));
+  std::vector<double> acc(n, 0.0);
+  for (int it = 0; it < iters + 1; ++it) {  // iteration 0 is an untimed warm-up
+    DFB_CUDA_OK(cudaEventRecord(ev[0], s));
+    for (int i = 0; i < n; ++i) {
+      r = p->ops[i](s);
+      if (r) return r;
+      if (it == 0) {
+        memset(&infos[i], 0, sizeof(dfb_op_info));
+        strncpy(infos[i].kind, g_note.kind, sizeof(infos[i].kind) - 1);
+        infos[i].M = g_note.M; infos[i].N = g_note.N; infos[i].K = g_note.K;
+        infos[i].splits = g_note.splits; infos[i].ctas = g_note.ctas;
+        infos[i].flops = g_note.flops; infos[i].bytes = g_note.bytes;
+      }
+      DFB_CUDA_OK(cudaEventRecord(ev[i + 1], s));
+    }
+    DFB_CUDA_OK(cudaStreamSynchronize(s));
+    if (it > 0)
+      for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        DFB_CUDA_OK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+        acc[i] += ms;
+      }
+  }
+  for (int i = 0; i < n; ++i) infos[i].ms = (float)(acc[i] / iters);
+  for (auto& e : ev) cudaEventDestroy(e);
   return 0;
 }
 

@@ -616,6 +616,13 @@ int igemm_launch(const IGemmPlan& plan, cudaStream_t stream) {
   kp.rows_per_sample = plan.e.rows_per_sample;
   kp.residual = plan.e.residual; kp.ld_res = plan.e.ld_res; kp.act = plan.e.act;
   kp.splits = plan.splits; kp.ws = plan.ws; kp.counters = plan.counters;
+  {
+    const double out_b = (plan.e.out_f32 ? 4.0 : 0.0) + (plan.e.out_f16 ? 2.0 : 0.0);
+    note(g.ntaps == 9 ? "igemm_conv3x3" : "igemm_linear", 2.0 * plan.M * plan.N * plan.K,
+         2.0 * plan.N * plan.K + 2.0 * plan.M * g.C + out_b * plan.M * plan.e.ldo +
+             (plan.e.residual ? 4.0 * plan.M * plan.e.ldo : 0.0),
+         plan.M, plan.N, plan.K, plan.splits, plan.tiles_m * plan.tiles_n * plan.splits);
+  }
   if (plan.BN == 64) return launch_t<64, 8>(plan, kp, stream);
   return launch_t<128, 6>(plan, kp, stream);
 }

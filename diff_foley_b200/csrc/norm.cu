@@ -105,6 +105,7 @@ int groupnorm_launch(const float* src0, int C0, const float* src1, int C1, int B
     set_error("groupnorm: group slab of " + std::to_string(smem) + " bytes exceeds shared memory");
     return -1;
   }
+  note("groupnorm", 0.0, (double)B * HW * C * (4.0 + 2.0 + (raw_out ? 2.0 : 0.0)), B * HW, C, 0, 1, 32 * B);
   groupnorm_kernel<<<dim3(32, B), GN_THREADS, smem, stream>>>(src0, C0, src1, C1, HW, gamma, beta,
                                                               eps, silu, out, raw_out);
   DFB_CUDA_OK(cudaGetLastError());
@@ -155,6 +156,7 @@ int layernorm_launch(const float* src, int rows, int C, const float* gamma, cons
     set_error("layernorm: C must be a multiple of 4");
     return -1;
   }
+  note("layernorm", 0.0, (double)rows * C * 6.0, rows, C, 0, 1, (rows + 7) / 8);
   layernorm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(src, rows, C, gamma, beta, eps, out);
   DFB_CUDA_OK(cudaGetLastError());
   return 0;

@@ -274,6 +274,28 @@ class UNetModelB200(nn.Module):
                     "dfb_unet_forward")
         return out.to(x.dtype)
 
+    @torch.no_grad()
+    def profile(self, x, timesteps, context, iters=5):
+        """Per-launch event-timed profile of one forward: list of dicts (kind, M, N, K, splits, ctas,
+        flops, bytes, ms).  Used by bench.py for the live roofline of the dominant kernel."""
+        h = self.engine(x.device)
+        n = x.shape[0]
+        xin = x.detach().float().contiguous()
+        ctx = context.detach().float().contiguous()
+        t = timesteps.to(torch.int64).contiguous()
+        out = torch.empty(n, self.out_channels, *self.latent_size, device=x.device)
+        lib = L.lib()
+        with torch.cuda.device(x.device):
+            L.check(lib.dfb_unet_set_context(h, L.ptr(ctx), n, ctx.shape[1], L.cur_stream()), "set_context")
+            cap = 4096
+            infos = (L.OpInfo * cap)()
+            n_ops = C.c_int(0)
+            L.check(lib.dfb_unet_profile(h, L.ptr(xin), 1, L.ptr(t), 0, L.ptr(out), n, iters, infos, cap,
+                                         C.byref(n_ops), L.cur_stream()), "dfb_unet_profile")
+        return [dict(kind=infos[i].kind.decode(), M=infos[i].M, N=infos[i].N, K=infos[i].K,
+                     splits=infos[i].splits, ctas=infos[i].ctas, flops=infos[i].flops,
+                     bytes=infos[i].bytes, ms=infos[i].ms) for i in range(n_ops.value)]
+
     def debug_taps(self, b_eff):
         """Block outputs of the last forward at this batch size as {name: NCHW tensor} (test aid)."""
         lib, out = L.lib(), {}

@@ -85,6 +85,19 @@ int dfb_ddim_sample(dfb_handle h, float* x_dev, const float* cond_dev, const flo
                     int n_clips, int ctx_len, float cfg_scale, int n_steps, const int64_t* timesteps,
                     const float* sqrt_one_minus_at, const float* sqrt_at, const float* sqrt_a_prev,
                     const float* dir_coef, float* pred_x0_dev, void* stream);
+/* Per-launch profile of one UNet forward: runs the plan for b_eff `iters` times with a CUDA event
+ * between consecutive launches (on `stream`) and returns, per launch, the kernel kind, its
+ * algorithmic FLOPs / bytes and the mean event-timed duration.  Context must have been set. */
+typedef struct dfb_op_info {
+  char kind[24];
+  int32_t M, N, K, splits, ctas;
+  double flops;
+  double bytes;
+  float ms;
+} dfb_op_info;
+int dfb_unet_profile(dfb_handle h, const float* x_dev, int x_repeat, const void* t_dev, int t_is_float,
+                     float* out_dev, int b_eff, int iters, dfb_op_info* infos, int cap, int* n_ops,
+                     void* stream);
 /* Debug/test aid: block outputs ("input_blocks.3", "middle_block", ...) of the plan for b_eff,
  * channels-last fp32 [b_eff, H, W, C].  With the environment variable DFB_DEBUG_TAPS=1 set before the
  * first forward every block output keeps its own buffer; otherwise only the skip-stack tensors
