@@ -34,6 +34,7 @@ static int ensure_scratch(size_t bytes) {
     g_ws = nullptr;
     g_ws_bytes = 0;
     DFB_CUDA_OK(cudaMalloc((void**)&g_ws, bytes));
+    DFB_CUDA_OK(cudaMemset(g_ws, 0, bytes));
     g_ws_bytes = bytes;
   }
   return 0;

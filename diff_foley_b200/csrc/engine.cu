@@ -871,6 +871,7 @@ static int build_plan(dfb_unet* e, int B, Plan** out) {
       if (b.need_ws > e->ws_bytes) {
         float* nw = nullptr;
         if (cudaMalloc((void**)&nw, b.need_ws) != cudaSuccess) { set_error("ws cudaMalloc failed"); return DFB_E_CUDA; }
+        cudaMemset(nw, 0, b.need_ws);  // the atomic split-K path keeps its accumulation tiles at zero between launches
         e->owned.push_back(nw);
         e->ws = nw;
         e->ws_bytes = b.need_ws;

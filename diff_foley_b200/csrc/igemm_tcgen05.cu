@@ -22,6 +22,7 @@
 // 107; attention_openai.py:233,244) and nn.Linear (attention_openai.py:40,60,161-168;
 // openai_unetmodel.py:218-224,507-511).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -53,6 +54,7 @@ struct IGemmKParams {
   int ld_res;
   int act;
   int splits;
+  int deterministic;
   float* ws;
   int* counters;
 };
@@ -298,18 +300,33 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         }
       }
     } else {
-      // ---- split-K: park the raw partial tile, last arriver reduces + runs the epilogue
-      float* wtile = p.ws + ((long)tile_lin * p.splits) * (BLOCK_M * BN);
-      float* mine = wtile + (long)blockIdx.z * (BLOCK_M * BN) + (long)r * BN;
+      // ---- split-K.  Default: every split CTA adds its partial tile into an L2-resident fp32
+      // accumulation tile with vector reductions (red.global.add.v4.f32: fire-and-forget, no
+      // serial latency chain); the last CTA to arrive (per-tile counter) reads the sums once, runs
+      // the epilogue and re-zeroes the tile.  DFB_DETERMINISTIC=1 selects the ordered variant:
+      // partial tiles parked side by side and summed in split order by the last arriver.
+      const bool det = (p.deterministic != 0);
+      const int nred = det ? p.splits : 1;
+      float* wtile = p.ws + (det ? ((long)tile_lin * p.splits) : (long)tile_lin) * (BLOCK_M * BN);
+      float* mine = wtile + (det ? (long)blockIdx.z * (BLOCK_M * BN) : 0L) + (long)r * BN;
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
         uint32_t raw[32];
         tmem_ld_32x32(taddr + c * 32, raw);
         tmem_ld_wait();
+        if (det) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<uint4*>(mine + c * 32 + j) =
-              make_uint4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(mine + c * 32 + j) =
+                make_uint4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
+        } else if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mine + c * 32 + j),
+                         "f"(__uint_as_float(raw[j])), "f"(__uint_as_float(raw[j + 1])),
+                         "f"(__uint_as_float(raw[j + 2])), "f"(__uint_as_float(raw[j + 3]))
+                         : "memory");
+        }
       }
       __threadfence();
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -322,19 +339,26 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (*last_flag) {
         __threadfence();
-        const float* rowp = wtile + (long)r * BN;
+        float* rowp = wtile + (long)r * BN;
         if (!geglu) {
 #pragma unroll 1
           for (int c = 0; c < NCH; ++c) {
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
-            for (int s = 0; s < p.splits; ++s) {
-              const float* q = rowp + (long)s * (BLOCK_M * BN) + c * 32;
+            if (row_ok || det) {
+              for (int s = 0; s < nred; ++s) {
+                float* q = rowp + (long)s * (BLOCK_M * BN) + c * 32;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 f = __ldcg(reinterpret_cast<const float4*>(q + j));
-                v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
+                for (int j = 0; j < 32; j += 4) {
+                  float4 f = __ldcg(reinterpret_cast<const float4*>(q + j));
+                  v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
+                }
+                if (!det) {
+#pragma unroll
+                  for (int j = 0; j < 32; j += 4)
+                    __stcg(reinterpret_cast<float4*>(q + j), make_float4(0.f, 0.f, 0.f, 0.f));
+                }
               }
             }
             const int nb = n0 + c * 32;
@@ -347,15 +371,24 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             float a[32], g[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) { a[j] = 0.f; g[j] = 0.f; }
-            for (int s = 0; s < p.splits; ++s) {
-              const float* qa = rowp + (long)s * (BLOCK_M * BN) + c * 32;
-              const float* qg = qa + BN / 2;
+            if (row_ok || det) {
+              for (int s = 0; s < nred; ++s) {
+                float* qa = rowp + (long)s * (BLOCK_M * BN) + c * 32;
+                float* qg = qa + BN / 2;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 f = __ldcg(reinterpret_cast<const float4*>(qa + j));
-                a[j] += f.x; a[j + 1] += f.y; a[j + 2] += f.z; a[j + 3] += f.w;
-                float4 h = __ldcg(reinterpret_cast<const float4*>(qg + j));
-                g[j] += h.x; g[j + 1] += h.y; g[j + 2] += h.z; g[j + 3] += h.w;
+                for (int j = 0; j < 32; j += 4) {
+                  float4 f = __ldcg(reinterpret_cast<const float4*>(qa + j));
+                  a[j] += f.x; a[j + 1] += f.y; a[j + 2] += f.z; a[j + 3] += f.w;
+                  float4 h = __ldcg(reinterpret_cast<const float4*>(qg + j));
+                  g[j] += h.x; g[j + 1] += h.y; g[j + 2] += h.z; g[j + 3] += h.w;
+                }
+                if (!det) {
+#pragma unroll
+                  for (int j = 0; j < 32; j += 4) {
+                    __stcg(reinterpret_cast<float4*>(qa + j), make_float4(0.f, 0.f, 0.f, 0.f));
+                    __stcg(reinterpret_cast<float4*>(qg + j), make_float4(0.f, 0.f, 0.f, 0.f));
+                  }
+                }
               }
             }
             if (row_ok) {
@@ -616,6 +649,14 @@ int igemm_launch(const IGemmPlan& plan, cudaStream_t stream) {
   kp.rows_per_sample = plan.e.rows_per_sample;
   kp.residual = plan.e.residual; kp.ld_res = plan.e.ld_res; kp.act = plan.e.act;
   kp.splits = plan.splits; kp.ws = plan.ws; kp.counters = plan.counters;
+  {
+    static int det = -1;
+    if (det < 0) {
+      const char* e = getenv("DFB_DETERMINISTIC");
+      det = (e && e[0] == '1') ? 1 : 0;
+    }
+    kp.deterministic = det;
+  }
   {
     const double out_b = (plan.e.out_f32 ? 4.0 : 0.0) + (plan.e.out_f16 ? 2.0 : 0.0);
     note(g.ntaps == 9 ? "igemm_conv3x3" : "igemm_linear", 2.0 * plan.M * plan.N * plan.K,
