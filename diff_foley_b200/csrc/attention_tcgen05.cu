@@ -1,0 +1,363 @@
+// attention_tcgen05.cu -- fused softmax(q k^T * scale) v for the UNet's self- and cross-attention on
+// the 5th-gen tensor cores (tcgen05) with both accumulators in TMEM.
+//
+// One CTA owns a 128-query tile of one (sample, head).  Per block of KB keys:
+//   S = Q K^T        tcgen05.mma, fp16 operands from shared memory, fp32 S[128 x KB] in TMEM (double
+//                    buffered: S_{j+1} is issued while the softmax warps work on S_j)
+//   P = softmax-blk  4 warps, one query row per thread (row = TMEM lane, no shuffles): tcgen05.ld,
+//                    running max / sum in registers, exp2 with the d^-0.5 scale folded in, P written
+//                    as fp16 into shared memory in the MMA's canonical K-major layout
+//   O += P V         tcgen05.mma with V as an MN-major B operand (no transposed copy of V); O[128 x d]
+//                    stays in TMEM for the whole key loop and is rescaled in place (tcgen05.ld/st)
+//                    only by warps whose running max actually moved
+// so the [B*8, Nq, Nk] score tensor the reference materialises in HBM (attention_openai.py:178-190:
+// einsum -> softmax -> einsum, 32 MB per sample at the 16x64 level) never exists.
+//
+// Operands are the fp16 projections written by the QKV GEMM epilogue (head h at columns h*dpad of
+// each row, dpad = head dim padded to a multiple of 16 with zero columns).  TMA loads them as one
+// (8 halves x rows) box per 16-byte chunk, which lands them in shared memory as
+// [chunk][row][8 halves] -- the un-swizzled canonical core-matrix layout (8 rows x 16 B contiguous)
+// that serves as K-major A/B operand (Q, K) *and* as MN-major B operand (V) without any shuffle.
+// The output is fp16 [B*Lq, heads*d], the A operand of the to_out GEMM -- the reference's
+// '(b h) n d -> b n (h d)' rearrange is free.
+//
+// warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = softmax / correction /
+// epilogue (TMEM sub-partition = warp_idx % 4).
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "dfb_internal.h"
+#include "dfb_ptx.cuh"
+
+namespace dfb {
+
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
+
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_BM = 128;  // queries per CTA
+
+struct AttParams {
+  __half* out;
+  int ldo;
+  int heads, Lq, Lk, d, dpad, KB, nblocks;
+  float scale_log2;  // d^-0.5 * log2(e)
+  int swap_lbo;      // debug: swap LBO/SBO of the un-swizzled descriptors
+};
+
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// smem carve-up (bytes), all tiles in the [chunk][row][8 halves] layout
+struct AttSmem {
+  int q_bytes, kv_tile_bytes, p_bytes;
+  int off_q, off_k[2], off_v[2], off_p[2], off_bar, total;
+};
+__host__ __device__ inline AttSmem att_smem_layout(int dpad, int KB) {
+  AttSmem s;
+  s.q_bytes = ATT_BM * dpad * 2;
+  s.kv_tile_bytes = KB * dpad * 2;
+  s.p_bytes = ATT_BM * KB * 2;
+  int o = 0;
+  s.off_q = o; o += s.q_bytes;
+  for (int i = 0; i < 2; ++i) { s.off_k[i] = o; o += s.kv_tile_bytes; s.off_v[i] = o; o += s.kv_tile_bytes; }
+  for (int i = 0; i < 2; ++i) { s.off_p[i] = o; o += s.p_bytes; }
+  s.off_bar = (o + 15) & ~15;
+  s.total = s.off_bar + 16 * 8 + 16;
+  return s;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttParams p) {
+  extern __shared__ uint8_t att_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_raw) + 127) &
+                                             ~static_cast<uintptr_t>(127));
+  const AttSmem L = att_smem_layout(p.dpad, p.KB);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;    // [2]
+  uint64_t* kv_empty = bars + 3;   // [2]
+  uint64_t* s_full = bars + 5;     // [2]
+  uint64_t* p_full = bars + 7;     // [2], 128 arrivals each
+  uint64_t* pv_done = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int b = bh / p.heads, h = bh % p.heads;
+  const int q0 = blockIdx.x * ATT_BM;
+  const int nb = p.nblocks;
+  const int KB = p.KB;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&kv_full[i], 1);
+        mbar_init(&kv_empty[i], 1);
+        mbar_init(&s_full[i], 1);
+        mbar_init(&p_full[i], 128);
+      }
+      mbar_init(pv_done, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_s[2] = {tmem_base, tmem_base + 128};
+  const uint32_t tm_o = tmem_base + 256;
+
+  if (warp == 0) {
+    // ======================================================================== TMA producer
+    if (lane == 0) {
+      // one 2-D box (8 halves x rows) per 16-byte chunk: chunk c lands at tile + c*rows*16
+      const int nch = p.dpad >> 3, col0 = h * p.dpad;
+      mbar_expect_tx(q_full, L.q_bytes);
+      for (int c = 0; c < nch; ++c)
+        tma_load_2d(smem + L.off_q + c * (ATT_BM * 16), &tmQ, q_full, col0 + 8 * c, b * p.Lq + q0);
+      for (int j = 0; j < nb; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[s], 2 * L.kv_tile_bytes);
+        for (int c = 0; c < nch; ++c) {
+          tma_load_2d(smem + L.off_k[s] + c * (KB * 16), &tmK, &kv_full[s], col0 + 8 * c, b * p.Lk + j * KB);
+          tma_load_2d(smem + L.off_v[s] + c * (KB * 16), &tmV, &kv_full[s], col0 + 8 * c, b * p.Lk + j * KB);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ========================================================================= MMA issuer
+    const uint32_t idesc_s = umma_idesc_f16(ATT_BM, KB, 0, 0);
+    const uint32_t idesc_o = umma_idesc_f16(ATT_BM, p.dpad, 0, 1);  // B = V is MN-major
+    const uint32_t q_lbo = ATT_BM * 16, k_lbo = KB * 16;
+    auto desc = [&](uint32_t addr, uint32_t lbo, uint32_t sbo) {
+      return p.swap_lbo ? umma_desc_nosw(addr, sbo, lbo) : umma_desc_nosw(addr, lbo, sbo);
+    };
+    const uint32_t sq = smem_u32(smem + L.off_q);
+    auto issue_s = [&](int j) {
+      const int s = j & 1;
+      const uint32_t sk = smem_u32(smem + L.off_k[s]);
+      for (int k = 0; k < p.dpad / 16; ++k)
+        umma_f16_ss(tm_s[s], desc(sq + k * 2 * q_lbo, q_lbo, 128), desc(sk + k * 2 * k_lbo, k_lbo, 128),
+                    idesc_s, k > 0 ? 1u : 0u);
+      umma_commit(&s_full[s]);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    if (lane == 0) issue_s(0);
+    __syncwarp();
+    for (int j = 0; j < nb; ++j) {
+      const int s = j & 1;
+      if (j + 1 < nb) {
+        const int s1 = (j + 1) & 1;
+        mbar_wait(&kv_full[s1], ((j + 1) >> 1) & 1);
+        // S buffer s1 was last read by the softmax of block j-1 (done once P_{j-1} is full)
+        if (j >= 1) mbar_wait(&p_full[s1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        if (lane == 0) issue_s(j + 1);
+        __syncwarp();
+      }
+      mbar_wait(&p_full[s], (j >> 1) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sp = smem_u32(smem + L.off_p[s]);
+        const uint32_t sv = smem_u32(smem + L.off_v[s]);
+        for (int k = 0; k < KB / 16; ++k)
+          umma_f16_ss(tm_o, desc(sp + k * 2 * q_lbo, q_lbo, 128),
+                      // V: MN-major; 8-key groups are 128 B apart (LBO), 8-column groups KB*16 B (SBO)
+                      desc(sv + k * 256, 128, k_lbo), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(pv_done);
+        umma_commit(&kv_empty[s]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ============================================================ softmax / correction / epilogue
+    const int sub = warp & 3;
+    const int r = sub * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)(sub * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nb; ++j) {
+      const int s = j & 1;
+      mbar_wait(&s_full[s], (j >> 1) & 1);
+      tc_fence_after();
+      const int kvalid = min(KB, p.Lk - j * KB);  // keys of this block that exist
+      // ---- pass 1: row max
+      float mx = -INFINITY;
+      for (int c = 0; c < KB; c += 16) {
+        uint32_t raw[16];
+        tmem_ld_32x16(tm_s[s] + lane_off + c, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c + i < kvalid) mx = fmaxf(mx, __uint_as_float(raw[i]));
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float alpha = exp2f(m_run - m_new);  // 0 on the first block (m_run = -inf)
+      // ---- pass 2: p = exp2(s*scale - m), row sum, fp16 P tile in the canonical K-major layout
+      uint8_t* prow = smem + L.off_p[s] + r * 16;
+      float psum = 0.f;
+      for (int c = 0; c < KB; c += 16) {
+        uint32_t raw[16];
+        tmem_ld_32x16(tm_s[s] + lane_off + c, raw);
+        tmem_ld_wait();
+        float e[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float v = exp2f(fmaf(__uint_as_float(raw[i]), p.scale_log2, -m_new));
+          e[i] = (c + i < kvalid) ? v : 0.f;
+          psum += e[i];
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          __half2 h0 = __floats2half2_rn(e[8 * g + 0], e[8 * g + 1]);
+          __half2 h1 = __floats2half2_rn(e[8 * g + 2], e[8 * g + 3]);
+          __half2 h2 = __floats2half2_rn(e[8 * g + 4], e[8 * g + 5]);
+          __half2 h3 = __floats2half2_rn(e[8 * g + 6], e[8 * g + 7]);
+          uint4 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+          u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(prow + ((c >> 3) + g) * (ATT_BM * 16)) = u;
+        }
+      }
+      l_run = l_run * alpha + psum;
+      m_run = m_new;
+      fence_proxy_async_smem();  // generic-proxy P stores -> visible to the tensor core (async proxy)
+      // ---- correction: O *= alpha, in TMEM, once the previous P V has landed
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+          for (int c = 0; c < p.dpad; c += 16) {
+            uint32_t raw[16];
+            tmem_ld_32x16(tm_o + lane_off + c, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
+            tmem_st_32x16(tm_o + lane_off + c, raw);
+          }
+          tmem_st_wait();
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&p_full[s]);
+    }
+    // ---- epilogue: O / l -> fp16 [row, h*d + c]
+    mbar_wait(pv_done, (nb - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.f / l_run;
+    const bool row_ok = (q0 + r) < p.Lq;
+    __half* orow = p.out + ((size_t)b * p.Lq + q0 + r) * p.ldo + h * p.d;
+    for (int c = 0; c < p.dpad; c += 16) {
+      uint32_t raw[16];
+      tmem_ld_32x16(tm_o + lane_off + c, raw);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          if (c + i < p.d)
+            *reinterpret_cast<__half2*>(orow + c + i) =
+                __floats2half2_rn(__uint_as_float(raw[i]) * inv, __uint_as_float(raw[i + 1]) * inv);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int attention_init() {
+  DFB_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   200 * 1024));
+  return 0;
+}
+
+// tensor maps are cached: the engine's buffers are stable, so each (pointer, geometry) is encoded once
+struct TmapKey {
+  const void* p; int ld, rows, dpad, box_rows;
+  bool operator<(const TmapKey& o) const {
+    return std::tie(p, ld, rows, dpad, box_rows) < std::tie(o.p, o.ld, o.rows, o.dpad, o.box_rows);
+  }
+};
+static std::map<TmapKey, CUtensorMap> g_tmaps;
+static std::mutex g_tmap_mu;
+
+static int get_tmap(CUtensorMap* out, const __half* base, int ld, long rows, int dpad, int box_rows) {
+  TmapKey key{base, ld, (int)rows, dpad, box_rows};
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  auto it = g_tmaps.find(key);
+  if (it != g_tmaps.end()) { *out = it->second; return 0; }
+  // plain 2-D view [rows, ld] fp16; box = 8 halves (one 16-byte chunk) x box_rows
+  uint64_t dims[2] = {(uint64_t)ld, (uint64_t)rows};
+  uint64_t strides[1] = {(uint64_t)ld * 2};
+  uint32_t box[2] = {8, (uint32_t)box_rows};
+  int rc = make_tmap_f16(out, base, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (rc) return rc;
+  if (g_tmaps.size() > 4096) g_tmaps.clear();
+  g_tmaps[key] = *out;
+  return 0;
+}
+
+int attention_launch(const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv,
+                     __half* out, int ldo, int B, int heads, int Lq, int Lk, int d, int dpad,
+                     float scale, cudaStream_t stream) {
+  if (d > 160 || (d & 1) || dpad < d || (dpad % 16) || (ldq % 8) || (ldk % 8) || (ldv % 8) || Lk < 1) {
+    set_error("attention: need even head dim <= 160, dpad a multiple of 16 and row strides multiple of 8");
+    return -1;
+  }
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) {
+    set_error("attention: q/k/v must be 16-byte aligned");
+    return -1;
+  }
+  AttParams p;
+  p.out = out; p.ldo = ldo; p.heads = heads; p.Lq = Lq; p.Lk = Lk; p.d = d; p.dpad = dpad;
+  const int kb_max = dpad > 96 ? 64 : 128;  // keeps Q + 2x(K,V) + 2xP under the shared-memory limit
+  p.KB = std::min(kb_max, (Lk + 15) / 16 * 16);
+  p.nblocks = (Lk + p.KB - 1) / p.KB;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  static int swap = -1;
+  if (swap < 0) {
+    const char* e = getenv("DFB_ATT_SWAP_LBO");
+    swap = (e && e[0] == '1') ? 1 : 0;
+  }
+  p.swap_lbo = swap;
+  CUtensorMap tq, tk, tv;
+  int rc = get_tmap(&tq, q, ldq, (long)B * Lq, dpad, ATT_BM);
+  if (!rc) rc = get_tmap(&tk, k, ldk, (long)B * Lk, dpad, p.KB);
+  if (!rc) rc = get_tmap(&tv, v, ldv, (long)B * Lk, dpad, p.KB);
+  if (rc) return rc;
+  const AttSmem L = att_smem_layout(dpad, p.KB);
+  dim3 grid((Lq + ATT_BM - 1) / ATT_BM, B * heads);
+  note("attention", 4.0 * B * heads * (double)Lq * Lk * d,
+       2.0 * B * heads * ((double)Lq * d * 2 + (double)Lk * d * 2), Lq, Lk, d, 1, grid.x * grid.y);
+  attention_tcgen05_kernel<<<grid, ATT_THREADS, L.total + 128, stream>>>(tq, tk, tv, p);
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dfb
