@@ -123,6 +123,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // q/k/v come from the preceding GEMM
+  pdl_launch_dependents();  // only after our own wait: at most two grids of the chain overlap
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_s[2] = {tmem_base, tmem_base + 128};
   const uint32_t tm_o = tmem_base + 256;
@@ -157,6 +159,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     auto issue_s = [&](int j) {
       const int s = j & 1;
       const uint32_t sk = smem_u32(smem + L.off_k[s]);
+#pragma unroll 1
       for (int k = 0; k < p.dpad / 16; ++k)
         umma_f16_ss(tm_s[s], desc(sq + k * 2 * q_lbo, q_lbo, 128), desc(sk + k * 2 * k_lbo, k_lbo, 128),
                     idesc_s, k > 0 ? 1u : 0u);
@@ -183,6 +186,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       if (lane == 0) {
         const uint32_t sp = smem_u32(smem + L.off_p[s]);
         const uint32_t sv = smem_u32(smem + L.off_v[s]);
+#pragma unroll 1
         for (int k = 0; k < KB / 16; ++k)
           umma_f16_ss(tm_o, desc(sp + k * 2 * q_lbo, q_lbo, 128),
                       // V: MN-major; 8-key groups are 128 B apart (LBO), 8-column groups KB*16 B (SBO)
@@ -205,6 +209,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       const int kvalid = min(KB, p.Lk - j * KB);  // keys of this block that exist
       // ---- pass 1: row max
       float mx = -INFINITY;
+#pragma unroll 1
       for (int c = 0; c < KB; c += 16) {
         uint32_t raw[16];
         tmem_ld_32x16(tm_s[s] + lane_off + c, raw);
@@ -218,6 +223,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       // ---- pass 2: p = exp2(s*scale - m), row sum, fp16 P tile in the canonical K-major layout
       uint8_t* prow = smem + L.off_p[s] + r * 16;
       float psum = 0.f;
+#pragma unroll 1
       for (int c = 0; c < KB; c += 16) {
         uint32_t raw[16];
         tmem_ld_32x16(tm_s[s] + lane_off + c, raw);
@@ -249,6 +255,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         mbar_wait(pv_done, (j - 1) & 1);
         tc_fence_after();
         if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll 1
           for (int c = 0; c < p.dpad; c += 16) {
             uint32_t raw[16];
             tmem_ld_32x16(tm_o + lane_off + c, raw);
@@ -269,6 +276,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     const float inv = 1.f / l_run;
     const bool row_ok = (q0 + r) < p.Lq;
     __half* orow = p.out + ((size_t)b * p.Lq + q0 + r) * p.ldo + h * p.d;
+#pragma unroll 1
     for (int c = 0; c < p.dpad; c += 16) {
       uint32_t raw[16];
       tmem_ld_32x16(tm_o + lane_off + c, raw);
@@ -355,7 +363,7 @@ int attention_launch(const __half* q, int ldq, const __half* k, int ldk, const _
   dim3 grid((Lq + ATT_BM - 1) / ATT_BM, B * heads);
   note("attention", 4.0 * B * heads * (double)Lq * Lk * d,
        2.0 * B * heads * ((double)Lq * d * 2 + (double)Lk * d * 2), Lq, Lk, d, 1, grid.x * grid.y);
-  attention_tcgen05_kernel<<<grid, ATT_THREADS, L.total + 128, stream>>>(tq, tk, tv, p);
+  DFB_CUDA_OK(launch_pdl(attention_tcgen05_kernel, dim3(grid), dim3(ATT_THREADS), L.total + 128, stream, tq, tk, tv, p));
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -1,11 +1,21 @@
 // capi.cu -- per-kernel C entry points (include/dfb.h, "per-kernel entry points").  They wrap the
 // same launchers the UNet engine uses, so the parity tests exercise exactly the shipped kernels.
+#include <cstdlib>
 #include <mutex>
 
 #include "../../include/dfb.h"
 #include "dfb_internal.h"
 
 namespace dfb {
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DFB_NO_PDL");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 int kernels_init() {
   static std::once_flag once;
@@ -44,14 +54,8 @@ static int run_igemm(const __half* a, const __half* w, int N, const IGemmGeom& g
                      int splits, cudaStream_t s) {
   int r = kernels_init();
   if (r) return r;
-  // worst case workspace: every tile split `splits` (or up to 32) ways
-  const size_t M = (size_t)g.B * g.T * g.H * g.W;
-  const size_t tiles_m = (M + 127) / 128 + 8;
-  const size_t bytes = tiles_m * ((N + 63) / 64) * 64 * 128 * sizeof(float) * (splits > 0 ? splits : 32);
-  r = ensure_scratch(std::min<size_t>(bytes, (size_t)1 << 30));
-  if (r) return r;
   IGemmPlan plan;
-  r = igemm_plan(&plan, a, w, N, g, ep, splits, g_ws, g_ws_bytes, g_counters, g_ncounters);
+  r = igemm_plan(&plan, a, w, N, g, ep, splits, nullptr, 0, nullptr, 0);
   if (r) return r;
   return igemm_launch(plan, s);
 }

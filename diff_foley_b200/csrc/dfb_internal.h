@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 
 namespace dfb {
 
@@ -36,6 +37,24 @@ inline void note(const char* kind, double flops, double bytes, int M = 0, int N 
                  int splits = 1, int ctas = 0) {
   g_note.kind = kind; g_note.flops = flops; g_note.bytes = bytes;
   g_note.M = M; g_note.N = N; g_note.K = K; g_note.splits = splits; g_note.ctas = ctas;
+}
+
+// Launch with the programmatic-dependent-launch attribute (DFB_NO_PDL=1 disables it).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 // one-time per-process kernel attribute setup (dynamic shared memory opt-in); idempotent

@@ -190,8 +190,44 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n, int a_mn_maj
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// --------------------------------------------------------- clusters / distributed shared memory
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> the same offset in the shared memory of CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
+}
+
+// ------------------------------------------------------------ programmatic dependent launch
+// Every kernel of the plan is launched with programmaticStreamSerialization: it may start while its
+// predecessor drains.  launch_dependents lets the successor's CTAs be scheduled early; wait blocks
+// until the predecessor grid has completed and its memory is visible, so it must precede the first
+// global access that depends on it (prologue work -- barrier init, TMEM alloc, descriptor prefetch --
+// runs before it and overlaps the predecessor's tail).  launch_dependents is only ever issued AFTER
+// the kernel's own wait, so at most two grids of the chain are in flight: with three, a grid that
+// started (and had its L1 invalidated) early could later hit L1 lines its SM cached for the middle
+// grid before the buffer was rewritten.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
-__device__ __forceinline__ float gelu_erf_f(float x) {
+// not inlined on purpose: erff expands to ~150 instructions and the GEGLU epilogue calls it per
+// element; inlining it 16x bloats the (cold-instruction-cache) GEMM kernel by tens of KB
+static __device__ __noinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
 }
 

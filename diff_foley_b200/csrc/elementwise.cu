@@ -11,6 +11,8 @@ namespace dfb {
 // timestep_embedding (reference util.py:151-171): [cos(t*f_j) | sin(t*f_j)], f_j = exp(-ln(1e4) j/half)
 __global__ void temb_kernel(const void* __restrict__ t, int t_is_float, int B, int dim,
                             __half* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int half_dim = dim / 2;
   if (i >= B * half_dim) return;
@@ -27,13 +29,15 @@ __global__ void temb_kernel(const void* __restrict__ t, int t_is_float, int B, i
 int temb_launch(const void* t, int t_is_float, int B, int dim, __half* out, cudaStream_t stream) {
   const int n = B * (dim / 2);
   note("temb", 0.0, (double)B * dim * 2.0);
-  temb_kernel<<<(n + 255) / 256, 256, 0, stream>>>(t, t_is_float, B, dim, out);
+  DFB_CUDA_OK(launch_pdl(temb_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, t, t_is_float, B, dim, out));
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
 __global__ void cast_f16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, size_t n4) {
+  pdl_wait();
+  pdl_launch_dependents();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n4; i += stride) {
@@ -54,8 +58,8 @@ int cast_f16_launch(const float* src, __half* dst, size_t n, cudaStream_t stream
   const size_t n4 = n / 4;
   const int blocks = (int)std::min<size_t>((n4 + 255) / 256, 148 * 8);
   note("cast_f16", 0.0, (double)n * 6.0);
-  cast_f16_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(src),
-                                              reinterpret_cast<uint2*>(dst), n4);
+  DFB_CUDA_OK(launch_pdl(cast_f16_kernel, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const float4*>(src),
+                                              reinterpret_cast<uint2*>(dst), n4));
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -64,6 +68,8 @@ int cast_f16_launch(const float* src, __half* dst, size_t n, cudaStream_t stream
 // fp16 cast: dst[b, y, x, :] = src[b, y/2, x/2, :]
 __global__ void upsample2x_f16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int B,
                                       int H, int W, int C4) {
+  pdl_wait();
+  pdl_launch_dependents();
   const size_t total = (size_t)B * 2 * H * 2 * W * C4;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -91,8 +97,8 @@ int upsample2x_f16_launch(const float* src, __half* dst, int B, int H, int W, in
   const size_t total = (size_t)B * 4 * H * W * (C / 4);
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
   note("upsample2x", 0.0, (double)total * 4 * (2.0 + 1.0));
-  upsample2x_f16_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(src),
-                                                    reinterpret_cast<uint2*>(dst), B, H, W, C / 4);
+  DFB_CUDA_OK(launch_pdl(upsample2x_f16_kernel, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const float4*>(src),
+                                                    reinterpret_cast<uint2*>(dst), B, H, W, C / 4));
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -101,6 +107,8 @@ int upsample2x_f16_launch(const float* src, __half* dst, int B, int H, int W, in
 // dst[(b, yo, xo), tap*C + c] = src[b, 2*yo + dy - 1, 2*xo + dx - 1, c]  (zero outside)
 __global__ void im2col_s2_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int B, int H,
                                  int W, int C4) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int Ho = H / 2, Wo = W / 2;
   const size_t total = (size_t)B * Ho * Wo * 9 * C4;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -131,8 +139,8 @@ int im2col_s2_launch(const float* src, __half* dst, int B, int H, int W, int C, 
   const size_t total = (size_t)B * (H / 2) * (W / 2) * 9 * (C / 4);
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
   note("im2col_s2", 0.0, (double)total * 4 * (2.0 + 1.0));
-  im2col_s2_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(src),
-                                               reinterpret_cast<uint2*>(dst), B, H, W, C / 4);
+  DFB_CUDA_OK(launch_pdl(im2col_s2_kernel, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const float4*>(src),
+                                               reinterpret_cast<uint2*>(dst), B, H, W, C / 4));
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -143,6 +151,8 @@ int im2col_s2_launch(const float* src, __half* dst, int B, int H, int W, int C, 
 __global__ void stem_conv_kernel(const float* __restrict__ x, int Bsrc, int Cin, int H, int W,
                                  const float* __restrict__ w, const float* __restrict__ bias, int Cout,
                                  float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int pix = blockIdx.x;  // b*H*W + y*W + x
   const int xq = pix % W, yq = (pix / W) % H, b = pix / (W * H);
   const int bs = b % Bsrc;
@@ -165,8 +175,8 @@ __global__ void stem_conv_kernel(const float* __restrict__ x, int Bsrc, int Cin,
 int stem_conv_launch(const float* x, int Bsrc, int B, int Cin, int H, int W, const float* w,
                      const float* bias, int Cout, float* out, cudaStream_t stream) {
   note("stem_conv", 2.0 * B * H * W * Cin * 9 * Cout, (double)B * H * W * Cout * 4.0);
-  stem_conv_kernel<<<B * H * W, 128, Cin * 9 * sizeof(float), stream>>>(x, Bsrc, Cin, H, W, w, bias,
-                                                                        Cout, out);
+  DFB_CUDA_OK(launch_pdl(stem_conv_kernel, dim3(B * H * W), dim3(128), Cin * 9 * sizeof(float), stream, x, Bsrc, Cin, H, W, w, bias,
+                                                                        Cout, out));
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -176,6 +186,8 @@ int stem_conv_launch(const float* x, int Bsrc, int B, int Cin, int H, int W, con
 __global__ void __launch_bounds__(256)
 head_conv_kernel(const __half* __restrict__ a, int B, int H, int W, int C, const float* __restrict__ w,
                  const float* __restrict__ bias, int Cout, float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int pix = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (pix >= B * H * W) return;
@@ -216,7 +228,7 @@ int head_conv_launch(const __half* a, int B, int H, int W, int C, const float* w
     return -1;
   }
   note("head_conv", 2.0 * B * H * W * C * 9 * Cout, (double)B * H * W * C * 2.0);
-  head_conv_kernel<<<(B * H * W + 7) / 8, 256, 0, stream>>>(a, B, H, W, C, w, bias, Cout, out);
+  DFB_CUDA_OK(launch_pdl(head_conv_kernel, dim3((B * H * W + 7) / 8), dim3(256), 0, stream, a, B, H, W, C, w, bias, Cout, out));
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -233,6 +245,8 @@ __global__ void ddim_update_kernel(const float* __restrict__ x, const float* __r
                                    float s, float sqrt_1mat, float sqrt_at, float sqrt_aprev,
                                    float dir_coef, float grad_coef, float* __restrict__ x_prev,
                                    float* __restrict__ pred_x0, size_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float e;
@@ -252,9 +266,9 @@ int ddim_update_launch(const float* x, const float* eps_uncond, const float* eps
                        float sqrt_a_prev, float dir_coef, float grad_coef, float* x_prev,
                        float* pred_x0, size_t n, cudaStream_t stream) {
   note("ddim_update", 0.0, (double)n * 20.0);
-  ddim_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+  DFB_CUDA_OK(launch_pdl(ddim_update_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, 
       x, eps_uncond, eps_cond, grad, cfg_scale, sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef,
-      grad_coef, x_prev, pred_x0, n);
+      grad_coef, x_prev, pred_x0, n));
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -14,9 +14,10 @@
 //   * epilogue (fused): + bias[n], + per-sample vector (timestep embedding), + fp32 residual,
 //     SiLU / ReLU / GEGLU gate, fp32 and/or fp16 stores.
 //   * split-K for the weight-streaming-bound deep layers (M <= 128 rows against 30-60 MB of
-//     weights): grid.z CTAs each stream a K range, park their fp32 partial tile in an L2-resident
-//     workspace and the last CTA to arrive (per-tile counter) reduces in fixed split order -- so the
-//     result is deterministic -- and runs the epilogue.
+//     weights): up to 8 CTAs along grid.z each stream a K range; they form a thread-block cluster,
+//     park their fp32 partial tiles in their own shared memory and reduce them through distributed
+//     shared memory in rank order (deterministic, no atomics, no global workspace), each CTA running
+//     the fused epilogue on its share of the tile's columns.
 //
 // Replaces (reference, all library calls): nn.Conv2d 3x3/1x1 (openai_unetmodel.py:204,230,241,
 // 107; attention_openai.py:233,244) and nn.Linear (attention_openai.py:40,60,161-168;
@@ -53,10 +54,7 @@ struct IGemmKParams {
   const float* residual;
   int ld_res;
   int act;
-  int splits;
-  int deterministic;
-  float* ws;
-  int* counters;
+  int splits;  // == cluster size along z (<= 8): the CTAs of one output tile reduce through DSMEM
 };
 
 template <int BN, int STAGES>
@@ -70,78 +68,83 @@ struct IGemmSmem {
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack to align the base to 1024 B
 };
 
-template <int BN>
-__device__ __forceinline__ void epilogue_store_chunk(const IGemmKParams& p, float (&v)[32],
-                                                     bool row_ok, long m, int b, int n_base,
-                                                     int out_col_base, int ncols_valid) {
-  // v: 32 consecutive accumulator columns of this thread's row (already summed over K).
-  if (!row_ok) return;
+// Epilogue on 16 consecutive columns of one accumulator row.  Kept deliberately compact (rolled
+// column-chunk loops, one code path): the kernel is launched ~200x per UNet forward between other
+// kernels, so it starts with a cold instruction cache every time -- a 100 KB fully unrolled
+// epilogue cost ~10 us per launch in instruction fetch alone.
+__device__ __forceinline__ void epilogue16(const IGemmKParams& p, float (&v)[16], long m, int bs,
+                                           int n_base) {
   if (p.bias != nullptr) {
+    const float4* bp = reinterpret_cast<const float4*>(p.bias + n_base);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < ncols_valid) v[j] += __ldg(p.bias + n_base + j);
+    for (int j = 0; j < 4; ++j) {
+      const float4 t = __ldg(bp + j);
+      v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+    }
   }
   if (p.rowvec != nullptr) {
-    const int bs = (p.rows_per_sample > 0) ? (int)(m / p.rows_per_sample) : b;
-    const float* rv = p.rowvec + (long)bs * p.ld_rowvec + n_base;
+    const float4* rp = reinterpret_cast<const float4*>(p.rowvec + (long)bs * p.ld_rowvec + n_base);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < ncols_valid) v[j] += __ldg(rv + j);
+    for (int j = 0; j < 4; ++j) {
+      const float4 t = __ldg(rp + j);
+      v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+    }
   }
   if (p.residual != nullptr) {
-    const float* rs = p.residual + m * p.ld_res + out_col_base;
-    if (ncols_valid == 32) {
+    const float4* rs = reinterpret_cast<const float4*>(p.residual + m * p.ld_res + n_base);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 r4 = *reinterpret_cast<const float4*>(rs + j);
-        v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols_valid) v[j] += rs[j];
+    for (int j = 0; j < 4; ++j) {
+      const float4 t = rs[j];
+      v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
     }
   }
   if (p.act == ACT_SILU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+    for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
   } else if (p.act == ACT_RELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
   }
   if (p.out_f32 != nullptr) {
-    float* o = p.out_f32 + m * p.ldo + out_col_base;
-    if (ncols_valid == 32) {
+    float4* o = reinterpret_cast<float4*>(p.out_f32 + m * p.ldo + n_base);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols_valid) o[j] = v[j];
-    }
+    for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   }
   if (p.out_f16 != nullptr) {
-    __half* o = p.out_f16 + m * p.ldo + out_col_base;
-    if (ncols_valid == 32) {
+    uint4* o = reinterpret_cast<uint4*>(p.out_f16 + m * p.ldo + n_base);
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        __half2 h0 = __floats2half2_rn(v[j], v[j + 1]);
-        __half2 h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
-        __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]);
-        __half2 h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
-        uint4 u;
-        u.x = *reinterpret_cast<uint32_t*>(&h0);
-        u.y = *reinterpret_cast<uint32_t*>(&h1);
-        u.z = *reinterpret_cast<uint32_t*>(&h2);
-        u.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(o + j) = u;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols_valid) o[j] = __float2half_rn(v[j]);
+    for (int j = 0; j < 2; ++j) {
+      __half2 h0 = __floats2half2_rn(v[8 * j], v[8 * j + 1]);
+      __half2 h1 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
+      __half2 h2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
+      __half2 h3 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
+      uint4 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+      u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+      o[j] = u;
     }
+  }
+}
+
+// GEGLU on 16 value columns + their 16 gate columns -> 16 fp16 outputs (attention_openai.py:42-44)
+__device__ __forceinline__ void epilogue16_geglu(const IGemmKParams& p, const float (&a)[16],
+                                                 const float (&g)[16], long m, int nbv, int nbg,
+                                                 int out_col) {
+  float o[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    o[j] = (a[j] + __ldg(p.bias + nbv + j)) * gelu_erf_f(g[j] + __ldg(p.bias + nbg + j));
+  uint4* dst = reinterpret_cast<uint4*>(p.out_f16 + m * p.ldo + out_col);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    __half2 h0 = __floats2half2_rn(o[8 * j], o[8 * j + 1]);
+    __half2 h1 = __floats2half2_rn(o[8 * j + 2], o[8 * j + 3]);
+    __half2 h2 = __floats2half2_rn(o[8 * j + 4], o[8 * j + 5]);
+    __half2 h3 = __floats2half2_rn(o[8 * j + 6], o[8 * j + 7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+    u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+    dst[j] = u;
   }
 }
 
@@ -158,7 +161,6 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -198,7 +200,26 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything above overlapped the predecessor's tail; operands are valid from here
+  pdl_launch_dependents();  // only after our own wait: at most two grids of the chain overlap
   const uint32_t tmem_base = *tmem_slot;
+  const bool geglu = (p.act == ACT_GEGLU);
+  const bool split = (p.splits > 1);
+  // output row owned by this thread when it acts as an epilogue thread (warps 2..5)
+  bool row_ok = false;
+  long m = 0;
+  int bs = 0;
+  if (warp >= 2) {
+    const int r = (warp & 3) * 32 + lane;
+    const int w_i = r % p.bw;
+    const int h_i = (r / p.bw) % p.bh;
+    const int t_i = (r / (p.bw * p.bh)) % p.bt;
+    const int b_i = r / (p.bw * p.bh * p.bt);
+    const int x = x0 + w_i, y = y0 + h_i, t = t0 + t_i, b = b0 + b_i;
+    row_ok = (x < p.W) && (y < p.H) && (t < p.T) && (b < p.B);
+    m = (((long)b * p.T + t) * p.H + y) * p.W + x;
+    bs = (p.rows_per_sample > 0) ? (int)(m / p.rows_per_sample) : b;
+  }
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -245,170 +266,104 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     // ========================================================================= epilogue
     const int sub = warp & 3;          // TMEM sub-partition this warp may read
     const int r = sub * 32 + lane;     // accumulator row (= TMEM lane) owned by this thread
-    const int w_i = r % p.bw;
-    const int h_i = (r / p.bw) % p.bh;
-    const int t_i = (r / (p.bw * p.bh)) % p.bt;
-    const int b_i = r / (p.bw * p.bh * p.bt);
-    const int x = x0 + w_i, y = y0 + h_i, t = t0 + t_i, b = b0 + b_i;
-    const bool row_ok = (x < p.W) && (y < p.H) && (t < p.T) && (b < p.B);
-    const long m = (((long)b * p.T + t) * p.H + y) * p.W + x;
     const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
-    const int tile_lin = blockIdx.y * gridDim.x + blockIdx.x;
-    constexpr int NCH = BN / 32;
-    const bool geglu = (p.act == ACT_GEGLU);
-
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-
-    if (p.splits == 1) {
+    if (!split) {
+      // NB: tcgen05.ld is warp-collective (.sync.aligned): every lane loads, stores are predicated
       if (!geglu) {
 #pragma unroll 1
-        for (int c = 0; c < NCH; ++c) {
-          uint32_t raw[32];
-          tmem_ld_32x32(taddr + c * 32, raw);
+        for (int c = 0; c < BN; c += 16) {
+          if (n0 + c >= p.N) break;
+          uint32_t raw[16];
+          tmem_ld_32x16(taddr + c, raw);
           tmem_ld_wait();
-          float v[32];
+          float v[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          const int nb = n0 + c * 32;
-          const int valid = min(32, p.N - nb);
-          if (valid > 0) epilogue_store_chunk<BN>(p, v, row_ok, m, b, nb, nb, valid);
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+          if (row_ok) epilogue16(p, v, m, bs, n0 + c);
         }
       } else {
-        // GEGLU: tile columns [0,BN/2) are the value half, [BN/2,BN) the gate half of the same
-        // BN/2 output features (weights were interleaved per tile when packed).
+        // tile columns [0,BN/2) are the value half, [BN/2,BN) the gate half of the same BN/2
+        // output features (weights were interleaved per tile when packed)
 #pragma unroll 1
-        for (int c = 0; c < NCH / 2; ++c) {
-          uint32_t rv[32], rg[32];
-          tmem_ld_32x32(taddr + c * 32, rv);
-          tmem_ld_32x32(taddr + BN / 2 + c * 32, rg);
+        for (int c = 0; c < BN / 2; c += 16) {
+          uint32_t ra[16], rg[16];
+          tmem_ld_32x16(taddr + c, ra);
+          tmem_ld_32x16(taddr + BN / 2 + c, rg);
           tmem_ld_wait();
-          if (row_ok) {
-            const int nbv = n0 + c * 32, nbg = n0 + BN / 2 + c * 32;
-            const int ob = blockIdx.x * (BN / 2) + c * 32;
-            __half* o = p.out_f16 + m * p.ldo + ob;
+          float a[16], g[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float a0 = __uint_as_float(rv[j]) + __ldg(p.bias + nbv + j);
-              float a1 = __uint_as_float(rv[j + 1]) + __ldg(p.bias + nbv + j + 1);
-              float g0 = __uint_as_float(rg[j]) + __ldg(p.bias + nbg + j);
-              float g1 = __uint_as_float(rg[j + 1]) + __ldg(p.bias + nbg + j + 1);
-              *reinterpret_cast<__half2*>(o + j) =
-                  __floats2half2_rn(a0 * gelu_erf_f(g0), a1 * gelu_erf_f(g1));
-            }
-          }
+          for (int j = 0; j < 16; ++j) { a[j] = __uint_as_float(ra[j]); g[j] = __uint_as_float(rg[j]); }
+          if (row_ok) epilogue16_geglu(p, a, g, m, n0 + c, n0 + BN / 2 + c, blockIdx.x * (BN / 2) + c);
         }
       }
     } else {
-      // ---- split-K.  Default: every split CTA adds its partial tile into an L2-resident fp32
-      // accumulation tile with vector reductions (red.global.add.v4.f32: fire-and-forget, no
-      // serial latency chain); the last CTA to arrive (per-tile counter) reads the sums once, runs
-      // the epilogue and re-zeroes the tile.  DFB_DETERMINISTIC=1 selects the ordered variant:
-      // partial tiles parked side by side and summed in split order by the last arriver.
-      const bool det = (p.deterministic != 0);
-      const int nred = det ? p.splits : 1;
-      float* wtile = p.ws + (det ? ((long)tile_lin * p.splits) : (long)tile_lin) * (BLOCK_M * BN);
-      float* mine = wtile + (det ? (long)blockIdx.z * (BLOCK_M * BN) : 0L) + (long)r * BN;
+      // split-K: park this CTA's partial tile in its own shared memory (the operand stages are dead
+      // once tmem_full fired) as [4-column group][row] float4, conflict-free for row-per-thread access
+      float4* stg = reinterpret_cast<float4*>(smem);
 #pragma unroll 1
-      for (int c = 0; c < NCH; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32(taddr + c * 32, raw);
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t raw[16];
+        tmem_ld_32x16(taddr + c, raw);
         tmem_ld_wait();
-        if (det) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<uint4*>(mine + c * 32 + j) =
-                make_uint4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
-        } else if (row_ok) {
+        for (int j = 0; j < 4; ++j)
+          stg[((c >> 2) + j) * BLOCK_M + r] =
+              make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                          __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+      }
+    }
+  }
+
+  if (split) {
+    // ---- split-K reduction through distributed shared memory.  The `splits` CTAs of one output
+    // tile form a thread-block cluster (cluster dims (1,1,splits)); after a cluster barrier each CTA
+    // reduces every splits-th 16-column chunk by reading all peers' parked tiles with
+    // ld.shared::cluster in rank order -- deterministic, no atomics, no HBM/L2 workspace -- and runs
+    // the fused epilogue on it.
+    cluster_sync_all();
+    if (warp >= 2) {
+      const int sub = warp & 3;
+      const int r = sub * 32 + lane;
+      const uint32_t stg_base = smem_u32(smem);
+      const int S = p.splits, rank = blockIdx.z;
+      auto load16 = [&](int c, float (&v)[16]) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mine + c * 32 + j),
-                         "f"(__uint_as_float(raw[j])), "f"(__uint_as_float(raw[j + 1])),
-                         "f"(__uint_as_float(raw[j + 2])), "f"(__uint_as_float(raw[j + 3]))
-                         : "memory");
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+#pragma unroll 1
+        for (int sidx = 0; sidx < S; ++sidx) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t local = stg_base + (uint32_t)((((c >> 2) + j) * BLOCK_M + r) * 16);
+            const float4 f = ld_dsmem_f4(mapa_shared(local, (uint32_t)sidx));
+            v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
+          }
         }
-      }
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) {
-        const int old = atomicAdd(p.counters + tile_lin, 1);
-        const int last = (old == p.splits - 1) ? 1 : 0;
-        if (last) p.counters[tile_lin] = 0;  // self-reset for the next launch
-        *last_flag = last;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (*last_flag) {
-        __threadfence();
-        float* rowp = wtile + (long)r * BN;
+      };
+      if (row_ok) {
         if (!geglu) {
 #pragma unroll 1
-          for (int c = 0; c < NCH; ++c) {
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-            if (row_ok || det) {
-              for (int s = 0; s < nred; ++s) {
-                float* q = rowp + (long)s * (BLOCK_M * BN) + c * 32;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  float4 f = __ldcg(reinterpret_cast<const float4*>(q + j));
-                  v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
-                }
-                if (!det) {
-#pragma unroll
-                  for (int j = 0; j < 32; j += 4)
-                    __stcg(reinterpret_cast<float4*>(q + j), make_float4(0.f, 0.f, 0.f, 0.f));
-                }
-              }
-            }
-            const int nb = n0 + c * 32;
-            const int valid = min(32, p.N - nb);
-            if (valid > 0) epilogue_store_chunk<BN>(p, v, row_ok, m, b, nb, nb, valid);
+          for (int q = rank; q < BN / 16; q += S) {
+            const int c = q * 16;
+            if (n0 + c >= p.N) break;
+            float v[16];
+            load16(c, v);
+            epilogue16(p, v, m, bs, n0 + c);
           }
         } else {
 #pragma unroll 1
-          for (int c = 0; c < NCH / 2; ++c) {
-            float a[32], g[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { a[j] = 0.f; g[j] = 0.f; }
-            if (row_ok || det) {
-              for (int s = 0; s < nred; ++s) {
-                float* qa = rowp + (long)s * (BLOCK_M * BN) + c * 32;
-                float* qg = qa + BN / 2;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  float4 f = __ldcg(reinterpret_cast<const float4*>(qa + j));
-                  a[j] += f.x; a[j + 1] += f.y; a[j + 2] += f.z; a[j + 3] += f.w;
-                  float4 h = __ldcg(reinterpret_cast<const float4*>(qg + j));
-                  g[j] += h.x; g[j + 1] += h.y; g[j + 2] += h.z; g[j + 3] += h.w;
-                }
-                if (!det) {
-#pragma unroll
-                  for (int j = 0; j < 32; j += 4) {
-                    __stcg(reinterpret_cast<float4*>(qa + j), make_float4(0.f, 0.f, 0.f, 0.f));
-                    __stcg(reinterpret_cast<float4*>(qg + j), make_float4(0.f, 0.f, 0.f, 0.f));
-                  }
-                }
-              }
-            }
-            if (row_ok) {
-              const int nbv = n0 + c * 32, nbg = n0 + BN / 2 + c * 32;
-              const int ob = blockIdx.x * (BN / 2) + c * 32;
-              __half* o = p.out_f16 + m * p.ldo + ob;
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                float a0 = a[j] + __ldg(p.bias + nbv + j);
-                float a1 = a[j + 1] + __ldg(p.bias + nbv + j + 1);
-                float g0 = g[j] + __ldg(p.bias + nbg + j);
-                float g1 = g[j + 1] + __ldg(p.bias + nbg + j + 1);
-                *reinterpret_cast<__half2*>(o + j) =
-                    __floats2half2_rn(a0 * gelu_erf_f(g0), a1 * gelu_erf_f(g1));
-              }
-            }
+          for (int q = rank; q < BN / 32; q += S) {
+            const int c = q * 16;
+            float a[16], g[16];
+            load16(c, a);
+            load16(BN / 2 + c, g);
+            epilogue16_geglu(p, a, g, m, n0 + c, n0 + BN / 2 + c, blockIdx.x * (BN / 2) + c);
           }
         }
       }
     }
+    cluster_sync_all();  // nobody's shared memory may go away while a peer is still reading it
   }
 
   // ---- teardown
@@ -514,10 +469,7 @@ static int num_sms() {
   return g_num_sms;
 }
 
-size_t igemm_ws_bytes(const IGemmPlan& plan) {
-  if (plan.splits <= 1) return 0;
-  return (size_t)plan.tiles_m * plan.tiles_n * plan.splits * BLOCK_M * plan.BN * sizeof(float);
-}
+size_t igemm_ws_bytes(const IGemmPlan&) { return 0; }  // split-K reduces through DSMEM
 
 int igemm_plan(IGemmPlan* plan, const __half* A, const __half* Wt, int N, const IGemmGeom& g,
                const IGemmEpilogue& e, int splits, float* ws, size_t ws_bytes, int* counters,
@@ -539,46 +491,45 @@ int igemm_plan(IGemmPlan* plan, const __half* A, const __half* Wt, int N, const 
   plan->M = g.B * g.T * g.H * g.W;
   plan->N = N;
   plan->K = g.ntaps * g.C;
+  if (splits > 8) splits = 8;  // cluster size limit (portable)
   const bool geglu = (e.act == ACT_GEGLU);
-  // tile width: 128 unless N is small or 64 divides it better
-  int BN = 128;
-  if (N <= 64 || (N % 128 != 0 && N % 64 == 0 && N < 512)) BN = 64;
-  if (geglu) BN = 128;
-  plan->BN = BN;
   const int tw = (g.W + g.bw - 1) / g.bw, th = (g.H + g.bh - 1) / g.bh,
             tt = (g.T + g.bt - 1) / g.bt, tb = (g.B + g.bb - 1) / g.bb;
   plan->tiles_m = tw * th * tt * tb;
-  plan->tiles_n = (N + BN - 1) / BN;
-  const int tiles = plan->tiles_m * plan->tiles_n;
   const int kb_total = g.ntaps * (g.C / BLOCK_K);
-  if (splits <= 0) {
-    // fill the machine once: split K until tiles*splits ~ #SMs, keep >= 4 k-blocks per CTA
-    splits = 1;
-    if (tiles < num_sms()) {
-      splits = num_sms() / tiles;
-      splits = std::min(splits, std::max(1, kb_total / 4));
-      splits = std::min(splits, 32);
-      splits = std::max(splits, 1);
+  // ---- tile width BN and split-K factor (= cluster size, <= 8).  Tiny cost model: a CTA moves one
+  // (A rows that exist + BN weight rows) x 128 B stage per k-block at ~55 GB/s (its share of L2
+  // bandwidth), pays ~1 us for a DSMEM reduction, and the grid runs in ceil(ctas / #SMs) waves.
+  {
+    const int nsm = num_sms();
+    const int rows_per_tile = std::min(BLOCK_M, plan->M);  // rows TMA really fetches (rest is zero fill)
+    double best = 1e30;
+    int best_bn = 128, best_s = 1;
+    const int bn_lo = (geglu ? 128 : 64), bn_hi = (N <= 64 ? 64 : 128);
+    for (int bn = bn_hi; bn >= bn_lo; bn /= 2) {
+      const int tiles = plan->tiles_m * ((N + bn - 1) / bn);
+      const int smax = (splits > 0) ? splits : 8;
+      for (int sp = (splits > 0 ? splits : 1); sp <= smax; ++sp) {
+        if (sp > kb_total) break;
+        const int kb_cta = (kb_total + sp - 1) / sp;
+        const double stage_kb = (rows_per_tile + bn) * 128.0 / 1024.0;
+        const double waves = std::ceil((double)tiles * sp / nsm);
+        const double t = waves * (kb_cta * stage_kb / 55.0 + (sp > 1 ? 1.0 : 0.0) + 0.05 * (bn / 16)) + 3.0;
+        if (t < best - 1e-9) { best = t; best_bn = bn; best_s = sp; }
+      }
     }
+    plan->BN = best_bn;
+    splits = best_s;
   }
-  splits = std::min(splits, kb_total);
+  const int BN = plan->BN;
+  plan->tiles_n = (N + BN - 1) / BN;
   plan->splits = splits;
   plan->ws = nullptr;
   plan->counters = nullptr;
-  if (splits > 1) {
-    if (igemm_ws_bytes(*plan) > ws_bytes || tiles > ncounters || ws == nullptr ||
-        counters == nullptr) {
-      set_error("igemm: split-K workspace too small (need " +
-                std::to_string(igemm_ws_bytes(*plan)) + " bytes, " + std::to_string(tiles) +
-                " counters)");
-      return -1;
-    }
-    plan->ws = ws;
-    plan->counters = counters;
-  }
+  (void)ws; (void)ws_bytes; (void)counters; (void)ncounters;  // split-K no longer needs global scratch
   if ((e.out_f16 && (e.ldo % 8)) || (e.out_f32 && (e.ldo % 4)) || (e.residual && (e.ld_res % 4)) ||
-      (N % 32) != 0) {
-    set_error("igemm: N must be a multiple of 32 and output/residual row strides 16-byte aligned");
+      (N % 16) != 0) {
+    set_error("igemm: N must be a multiple of 16 and output/residual row strides 16-byte aligned");
     return -1;
   }
   if (e.out_f16 == nullptr && e.out_f32 == nullptr) {
@@ -624,10 +575,21 @@ int igemm_init() {
 template <int BN, int STAGES>
 static int launch_t(const IGemmPlan& plan, const IGemmKParams& kp, cudaStream_t stream) {
   using L = IGemmSmem<BN, STAGES>;
-  dim3 grid(plan.tiles_n, plan.tiles_m, plan.splits);
-  igemm_tcgen05_kernel<BN, STAGES><<<grid, IGEMM_THREADS, L::DYN_BYTES, stream>>>(plan.tmA,
-                                                                                   plan.tmW, kp);
-  DFB_CUDA_OK(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(plan.tiles_n, plan.tiles_m, plan.splits);
+  cfg.blockDim = dim3(IGEMM_THREADS);
+  cfg.dynamicSmemBytes = L::DYN_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;  // the K-splits of a tile share a cluster
+  attr[1].val.clusterDim.x = 1;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = plan.splits;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  DFB_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_tcgen05_kernel<BN, STAGES>, plan.tmA, plan.tmW, kp));
   return 0;
 }
 
@@ -648,15 +610,7 @@ int igemm_launch(const IGemmPlan& plan, cudaStream_t stream) {
   kp.bias = plan.e.bias; kp.rowvec = plan.e.rowvec; kp.ld_rowvec = plan.e.ld_rowvec;
   kp.rows_per_sample = plan.e.rows_per_sample;
   kp.residual = plan.e.residual; kp.ld_res = plan.e.ld_res; kp.act = plan.e.act;
-  kp.splits = plan.splits; kp.ws = plan.ws; kp.counters = plan.counters;
-  {
-    static int det = -1;
-    if (det < 0) {
-      const char* e = getenv("DFB_DETERMINISTIC");
-      det = (e && e[0] == '1') ? 1 : 0;
-    }
-    kp.deterministic = det;
-  }
+  kp.splits = plan.splits;
   {
     const double out_b = (plan.e.out_f32 ? 4.0 : 0.0) + (plan.e.out_f16 ? 2.0 : 0.0);
     note(g.ntaps == 9 ? "igemm_conv3x3" : "igemm_linear", 2.0 * plan.M * plan.N * plan.K,

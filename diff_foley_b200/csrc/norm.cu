@@ -40,6 +40,8 @@ groupnorm_kernel(const float* __restrict__ src0, int C0, const float* __restrict
                  float eps, int silu, __half* __restrict__ out, __half* __restrict__ raw_out) {
   extern __shared__ float slab[];  // [HW][cpg]
   __shared__ float red[GN_THREADS / 32];
+  pdl_wait();
+  pdl_launch_dependents();
   const int C = C0 + C1;
   const int cpg = C / 32;
   const int hp = cpg >> 1;  // channel pairs per pixel
@@ -106,8 +108,8 @@ int groupnorm_launch(const float* src0, int C0, const float* src1, int C1, int B
     return -1;
   }
   note("groupnorm", 0.0, (double)B * HW * C * (4.0 + 2.0 + (raw_out ? 2.0 : 0.0)), B * HW, C, 0, 1, 32 * B);
-  groupnorm_kernel<<<dim3(32, B), GN_THREADS, smem, stream>>>(src0, C0, src1, C1, HW, gamma, beta,
-                                                              eps, silu, out, raw_out);
+  DFB_CUDA_OK(launch_pdl(groupnorm_kernel, dim3(dim3(32, B)), dim3(GN_THREADS), smem, stream, src0, C0, src1, C1, HW, gamma, beta,
+                                                              eps, silu, out, raw_out));
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -116,6 +118,8 @@ int groupnorm_launch(const float* src0, int C0, const float* src1, int C1, int B
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ src, int rows, int C, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __half* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -157,7 +161,7 @@ int layernorm_launch(const float* src, int rows, int C, const float* gamma, cons
     return -1;
   }
   note("layernorm", 0.0, (double)rows * C * 6.0, rows, C, 0, 1, (rows + 7) / 8);
-  layernorm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(src, rows, C, gamma, beta, eps, out);
+  DFB_CUDA_OK(launch_pdl(layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, src, rows, C, gamma, beta, eps, out));
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
 }
