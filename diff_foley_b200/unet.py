@@ -55,6 +55,9 @@ class _Box(nn.Module):
         self.add_module(str(name), mod)
         return mod
 
+    def __getitem__(self, i):
+        return self._modules[str(i)]
+
 
 def _res(cin, cout, time_dim):
     b = _Box()

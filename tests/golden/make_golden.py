@@ -140,6 +140,67 @@ def gen_ddim(name, cfg, seed, n_clips, steps, scale, use_real_ldm=False):
     print(f"{name}: latent rms {float(samples.pow(2).mean().sqrt()):.4f} ({time.time() - t0:.1f}s)")
 
 
+def ref_classifier(cfg):
+    from diff_foley.modules.double_guidance.alignment_backbone import Classifier_Backbone
+    m = Classifier_Backbone(image_size=32, in_channels=cfg["in_channels"], out_channels=cfg["out_channels"],
+                            model_channels=cfg["model_channels"],
+                            attention_resolutions=list(cfg["attention_resolutions"]),
+                            num_res_blocks=cfg["num_res_blocks"], channel_mult=list(cfg["channel_mult"]),
+                            num_heads=cfg["num_heads"], use_spatial_transformer=True, transformer_depth=1,
+                            context_dim=cfg["context_dim"], use_checkpoint=True, legacy=False)
+    return m.eval()
+
+
+def gen_classifier(name, cfg, seed, b, ctx_len):
+    """Classifier_Backbone probabilities + the reference's own cal_classifier_loglikelihood_grad."""
+    from diff_foley.models.diffusion.ddim import DDIMSampler
+    from oracle import classifier_oracle
+    sd = classifier_oracle.seeded_state_dict(cfg, seed)
+    m = ref_classifier(cfg)
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed + 50)
+    x = torch.randn(b, 4, 16, 64, generator=g)
+    feats = torch.nn.functional.normalize(torch.randn(b, ctx_len, cfg["context_dim"], generator=g), dim=-1)
+    t = torch.tensor([961, 41, 500, 1][:b], dtype=torch.long)
+    with torch.no_grad():
+        prob = m(x, timesteps=t, context=feats)
+    wrapper = lambda x_in, t, video_feat: m(x_in, timesteps=t, context=video_feat)
+    grad = DDIMSampler.cal_classifier_loglikelihood_grad(None, wrapper, x, t, feats, classifier_guide_scale=50.0)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), x=x.numpy(), t=t.numpy(), feats=feats.numpy(),
+                        prob=prob.numpy(), grad=grad.numpy(), seed=np.int64(seed))
+    print(f"{name}: prob {prob.flatten().tolist()} grad rms {float(grad.pow(2).mean().sqrt()):.4e}")
+
+
+def gen_ddim_classifier(name, ucfg, ccfg, seed, n_clips, steps, scale, cscale):
+    """DDIMSampler.sample_with_classifier (ddim.py:115-176) on CPU: CFG + classifier guidance."""
+    t0 = time.time()
+    from diff_foley.models.diffusion.ddim import DDIMSampler
+    from oracle import classifier_oracle
+
+    class CpuDDIM(DDIMSampler):
+        def register_buffer(self, name, attr):
+            setattr(self, name, attr)
+
+    unet = ref_unet(ucfg)
+    unet.load_state_dict(unet_oracle.seeded_state_dict(ucfg, seed), strict=True)
+    clf = ref_classifier(ccfg)
+    clf.load_state_dict(classifier_oracle.seeded_state_dict(ccfg, seed + 1), strict=True)
+    classifier = lambda x_in, t, video_feat: clf(x_in, timesteps=t, context=video_feat)
+    g = torch.Generator().manual_seed(seed + 3000)
+    x_T = torch.randn(n_clips, 4, ucfg["latent_h"], ucfg["latent_w"], generator=g)
+    cond = torch.randn(n_clips, ucfg["context_len"], ucfg["context_dim"], generator=g)
+    feats = torch.nn.functional.normalize(torch.randn(n_clips, 33, ccfg["context_dim"], generator=g), dim=-1)
+    sampler = CpuDDIM(_StubLDM(unet))
+    samples, _ = sampler.sample_with_classifier(
+        S=steps, batch_size=n_clips, shape=(4, ucfg["latent_h"], ucfg["latent_w"]), conditioning=cond,
+        origin_cond=feats, eta=0.0, verbose=False, x_T=x_T, unconditional_guidance_scale=scale,
+        unconditional_conditioning=torch.zeros_like(cond), classifier=classifier, classifier_guide_scale=cscale)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), x_T=x_T.numpy(), cond=cond.numpy(), feats=feats.numpy(),
+                        samples=samples.numpy(), seed=np.int64(seed), steps=np.int64(steps),
+                        scale=np.float32(scale), cscale=np.float32(cscale))
+    print(f"{name}: latent rms {float(samples.pow(2).mean().sqrt()):.4f} ({time.time() - t0:.1f}s)")
+
+
 SMALL = unet_oracle.small_unet_cfg()                       # 64 ch, heads 4 -> head dims 16/32/64
 SMALL_ODD = unet_oracle.small_unet_cfg(model_channels=128, channel_mult=(1, 2), num_heads=8,
                                        context_dim=64, latent_h=8, latent_w=16, context_len=33,
@@ -156,6 +217,11 @@ if __name__ == "__main__":
     gen_unet("unet_small_odd", SMALL_ODD, 3, 2, [1, 1], ("input_blocks.1", "middle_block"))
     gen_ddim("ddim_small", SMALL, 1, 2, 25, 4.5)
     gen_ddim("ddim_small_ldm", SMALL, 4, 1, 5, 4.5, use_real_ldm=True)
+    from oracle import classifier_oracle
+    CLF_SMALL = dict(classifier_oracle.DIFF_FOLEY_CLASSIFIER, model_channels=64, num_heads=4, context_dim=64)
+    gen_classifier("classifier_small", CLF_SMALL, 5, 3, 33)
+    gen_classifier("classifier_full", classifier_oracle.DIFF_FOLEY_CLASSIFIER, 6, 2, 33)
+    gen_ddim_classifier("ddim_classifier_small", SMALL, CLF_SMALL, 9, 2, 25, 4.5, 50.0)
     if which == "all":
         gen_unet("unet_full", FULL, 7, 2, [961, 961])
         gen_unet("unet_full_t41", FULL, 7, 2, [41, 41])

@@ -100,3 +100,40 @@ def test_ddim_step_linearity():
     e = eu + 4.5 * (ec - eu)
     assert torch.allclose(p0 * float(c["sqrt_at"][3]) + float(c["sqrt_one_minus_at"][3]) * e, x, atol=1e-5)
     assert torch.allclose(xp, float(c["sqrt_a_prev"][3]) * p0 + float(c["dir_coef"][3]) * e, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------- classifier (row a15)
+from oracle import classifier_oracle  # noqa: E402
+
+CLF_SMALL = dict(classifier_oracle.DIFF_FOLEY_CLASSIFIER, model_channels=64, num_heads=4, context_dim=64)
+
+
+@pytest.mark.parametrize("name,cfg", [("classifier_small", CLF_SMALL),
+                                      ("classifier_full", classifier_oracle.DIFF_FOLEY_CLASSIFIER)])
+def test_classifier_oracle_matches_reference(name, cfg):
+    g = load(name)
+    sd = classifier_oracle.seeded_state_dict(cfg, int(g["seed"]))
+    x, t, f = (torch.from_numpy(g[k]) for k in ("x", "t", "feats"))
+    with torch.no_grad():
+        prob = classifier_oracle.classifier_forward(sd, cfg, x, t, f)
+    assert rel_l2(prob, g["prob"]) < 1e-6
+    grad = classifier_oracle.loglikelihood_grad(sd, cfg, x, t, f, 50.0)
+    assert rel_l2(grad, g["grad"]) < 1e-4
+
+
+def test_classifier_module_matches_oracle_and_keys():
+    """The product-side classifier mirror (torch autograd, see diff_foley_b200/classifier.py) has the
+    reference's parameter names and computes the same function as the oracle."""
+    from diff_foley_b200.classifier import ClassifierBackboneB200
+    cfg = CLF_SMALL
+    m = ClassifierBackboneB200(image_size=32, in_channels=4, out_channels=1, model_channels=cfg["model_channels"],
+                               attention_resolutions=list(cfg["attention_resolutions"]), num_res_blocks=1,
+                               channel_mult=list(cfg["channel_mult"]), num_heads=cfg["num_heads"],
+                               use_spatial_transformer=True, transformer_depth=1, context_dim=cfg["context_dim"],
+                               use_checkpoint=True, legacy=False)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == dict(classifier_oracle.classifier_param_shapes(cfg))
+    g = load("classifier_small")
+    m.load_state_dict(classifier_oracle.seeded_state_dict(cfg, int(g["seed"])))
+    x, t, f = (torch.from_numpy(g[k]) for k in ("x", "t", "feats"))
+    with torch.no_grad():
+        assert rel_l2(m(x, timesteps=t, context=f), g["prob"]) < 1e-6
