@@ -226,3 +226,27 @@ if __name__ == "__main__":
         gen_unet("unet_full", FULL, 7, 2, [961, 961])
         gen_unet("unet_full_t41", FULL, 7, 2, [41, 41])
         gen_ddim("ddim_full", FULL, 7, 1, 25, 4.5)
+
+
+def gen_vae_decode(name="vae_decode", seed=21):
+    """decoded image of the reference-sampled latent (ddim_full.npz) through the reference's own
+    AutoencoderKL.decode with seeded decoder weights: the north-star tolerance is stated on mel =
+    channel 0 of this."""
+    from diff_foley.models.autoencoder import AutoencoderKL
+    from oracle import vae_oracle
+    with open(os.path.join(REF, "inference/config/Stage2_LDM.yaml")) as f:
+        y = yaml.safe_load(f)["model"]["params"]["first_stage_config"]["params"]
+    vae = AutoencoderKL(**y).eval()
+    sd = vae_oracle.seeded_state_dict(seed)
+    missing, unexpected = vae.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith(("encoder.", "quant_conv.", "loss.")) for k in missing), (missing, unexpected)
+    z = torch.from_numpy(np.load(os.path.join(HERE, "ddim_full.npz"))["samples"])
+    with torch.no_grad():
+        img = vae.decode(z / 0.18215)             # decode_first_stage, ddpm.py:739-797
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), z=z.numpy(), mel=img[:, 0].numpy(),
+                        img_rms=np.float32(img.pow(2).mean().sqrt()), seed=np.int64(seed))
+    print(f"{name}: image {tuple(img.shape)} mel rms {float(img[:, 0].pow(2).mean().sqrt()):.4f}")
+
+
+if __name__ == "__main__" and (len(sys.argv) < 2 or sys.argv[1] in ("all", "vae")):
+    gen_vae_decode()

@@ -137,3 +137,13 @@ def test_classifier_module_matches_oracle_and_keys():
     x, t, f = (torch.from_numpy(g[k]) for k in ("x", "t", "feats"))
     with torch.no_grad():
         assert rel_l2(m(x, timesteps=t, context=f), g["prob"]) < 1e-6
+
+
+def test_vae_decode_oracle_matches_reference():
+    """oracle/vae_oracle.py vs the reference's AutoencoderKL.decode on the reference-sampled latent."""
+    from oracle import vae_oracle
+    g = load("vae_decode")
+    sd = vae_oracle.seeded_state_dict(int(g["seed"]))
+    img = vae_oracle.decode_first_stage(sd, torch.from_numpy(g["z"]))
+    assert img.shape == (1, 3, 128, 512)
+    assert rel_l2(img[:, 0], g["mel"]) < 1e-5
