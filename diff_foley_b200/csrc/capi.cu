@@ -101,6 +101,38 @@ int dfb_conv3x3(const void* a, const void* w, int B, int H, int W, int C, int N,
                    (cudaStream_t)stream);
 }
 
+int dfb_conv_taps(const void* a, const void* w, int B, int T, int H, int W, int C, int N, int kt, int kh,
+                  int kw, const float* bias, const void* residual_f16, int act, float* out_f32,
+                  void* out_f16, int splits, void* stream) {
+  if (!a || !w || kt * kh * kw > 9 || kt < 1 || kh < 1 || kw < 1 || !(kt & 1) || !(kh & 1) || !(kw & 1)) {
+    set_error("dfb_conv_taps: odd kernel extents with kt*kh*kw <= 9 required");
+    return DFB_E_INVALID;
+  }
+  IGemmEpilogue ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.out_f32 = out_f32;
+  ep.out_f16 = (__half*)out_f16;
+  ep.ldo = N;
+  ep.bias = bias;
+  ep.residual_f16 = (const __half*)residual_f16;
+  ep.ld_res = N;
+  ep.act = act;
+  return run_igemm((const __half*)a, (const __half*)w, N, conv_taps_geom(B, T, H, W, C, kt, kh, kw), ep,
+                   splits, (cudaStream_t)stream);
+}
+
+int dfb_im2col_f16(const void* src, void* dst, int NI, int H, int W, int C, int kh, int kw, int stride,
+                   int pad, int Kpad, void* stream) {
+  return im2col_f16_launch((const __half*)src, (__half*)dst, NI, H, W, C, kh, kw, stride, pad, Kpad,
+                           (cudaStream_t)stream);
+}
+
+int dfb_pool2d_f16(const void* src, void* dst, int NI, int H, int W, int C, int kh, int kw, int sh, int sw,
+                   int ph, int pw, int is_max, void* stream) {
+  return pool2d_f16_launch((const __half*)src, (__half*)dst, NI, H, W, C, kh, kw, sh, sw, ph, pw, is_max,
+                           (cudaStream_t)stream);
+}
+
 int dfb_groupnorm(const float* src0, int C0, const float* src1, int C1, int B, int HW, const float* gamma,
                   const float* beta, float eps, int silu, void* out, void* raw, void* stream) {
   int r = kernels_init();

@@ -87,6 +87,7 @@ struct IGemmEpilogue {
   int ld_rowvec;
   int rows_per_sample;      // rows (output positions) per sample, for rowvec
   const float* residual;    // optional fp32 [M, ld_res]
+  const __half* residual_f16;  // optional fp16 [M, ld_res] (CAVP ResNet identity path)
   int ld_res;
   int act;                  // ACT_*
 };
@@ -109,6 +110,8 @@ int igemm_plan(IGemmPlan* plan, const __half* A, const __half* Wt, int N, const 
                int ncounters);
 size_t igemm_ws_bytes(const IGemmPlan& plan);
 int igemm_launch(const IGemmPlan& plan, cudaStream_t stream);
+// geometry for a "same"-padded stride-1 conv with a (kt,kh,kw) kernel over [B,T,H,W,C] (kt*kh*kw <= 9)
+IGemmGeom conv_taps_geom(int B, int T, int H, int W, int C, int kt, int kh, int kw);
 // convenience geometry for a plain [M,K] x [N,K]^T GEMM
 IGemmGeom gemm_geom(int M, int K);
 // geometry for a 3x3 / pad 1 / stride 1 conv over [B,H,W,C]
@@ -145,6 +148,13 @@ int stem_conv_launch(const float* x, int Bsrc, int B, int Cin, int H, int W, con
 // head conv: fp16 NHWC [B,H,W,C] (already GN+SiLU'd) -> NCHW fp32 [B,Cout,H,W]
 int head_conv_launch(const __half* a, int B, int H, int W, int C, const float* w,
                      const float* bias, int Cout, float* out, cudaStream_t stream);
+// ---- fp16 channels-last helpers used by the CAVP encoders
+// generic im2col: [NI,H,W,C] -> [NI*Ho*Wo, Kpad], k = (ky*kw+kx)*C + c, zero beyond kh*kw*C
+int im2col_f16_launch(const __half* src, __half* dst, int NI, int H, int W, int C, int kh, int kw,
+                      int stride, int pad, int Kpad, cudaStream_t stream);
+// max / average pooling over [NI,H,W,C]; window (kh,kw), stride (sh,sw), padding (ph,pw)
+int pool2d_f16_launch(const __half* src, __half* dst, int NI, int H, int W, int C, int kh, int kw,
+                      int sh, int sw, int ph, int pw, int is_max, cudaStream_t stream);
 // fused classifier-free-guidance combine + DDIM update (ddim.py:241-273 of the reference)
 int ddim_update_launch(const float* x, const float* eps_uncond, const float* eps_cond,
                        const float* grad, float cfg_scale, float sqrt_one_minus_at, float sqrt_at,

@@ -234,6 +234,103 @@ int head_conv_launch(const __half* a, int B, int H, int W, int C, const float* w
 }
 
 // ---------------------------------------------------------------------------------------------
+// CAVP helpers (fp16 channels-last).  8 halves (16 B) per thread.
+__global__ void im2col_f16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int NI, int H,
+                                  int W, int C8, int kh, int kw, int stride, int pad, int Ho, int Wo,
+                                  int K8) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const size_t total = (size_t)NI * Ho * Wo * K8;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (; i < total; i += step) {
+    const int k8 = (int)(i % K8);
+    size_t r = i / K8;
+    const int xo = (int)(r % Wo); r /= Wo;
+    const int yo = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    const int tap = k8 / C8, c8 = k8 - tap * C8;
+    if (tap < kh * kw) {
+      const int y = yo * stride + tap / kw - pad, x = xo * stride + tap % kw - pad;
+      if (y >= 0 && y < H && x >= 0 && x < W) v = src[(((size_t)n * H + y) * W + x) * C8 + c8];
+    }
+    dst[i] = v;
+  }
+}
+
+int im2col_f16_launch(const __half* src, __half* dst, int NI, int H, int W, int C, int kh, int kw,
+                      int stride, int pad, int Kpad, cudaStream_t stream) {
+  if (C % 8 || Kpad % 8 || Kpad < kh * kw * C) {
+    set_error("im2col_f16: C and Kpad must be multiples of 8 and Kpad >= kh*kw*C");
+    return -1;
+  }
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  const size_t total = (size_t)NI * Ho * Wo * (Kpad / 8);
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  note("im2col_f16", 0.0, (double)total * 32.0);
+  DFB_CUDA_OK(launch_pdl(im2col_f16_kernel, dim3(blocks), dim3(256), 0, stream,
+                         reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), NI, H, W, C / 8,
+                         kh, kw, stride, pad, Ho, Wo, Kpad / 8));
+  return 0;
+}
+
+__global__ void pool2d_f16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int NI, int H,
+                                  int W, int C8, int kh, int kw, int sh, int sw, int ph, int pw, int Ho,
+                                  int Wo, int is_max) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const size_t total = (size_t)NI * Ho * Wo * C8;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (; i < total; i += step) {
+    const int c8 = (int)(i % C8);
+    size_t r = i / C8;
+    const int xo = (int)(r % Wo); r /= Wo;
+    const int yo = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = is_max ? -INFINITY : 0.f;
+    for (int a = 0; a < kh; ++a)
+      for (int b = 0; b < kw; ++b) {
+        const int y = yo * sh + a - ph, x = xo * sw + b - pw;
+        if (y < 0 || y >= H || x < 0 || x >= W) continue;  // max: padding ignored; avg: windows never pad here
+        const uint4 u = src[(((size_t)n * H + y) * W + x) * C8 + c8];
+        const __half2* hp = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(hp[j]);
+          if (is_max) { acc[2 * j] = fmaxf(acc[2 * j], f.x); acc[2 * j + 1] = fmaxf(acc[2 * j + 1], f.y); }
+          else { acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+        }
+      }
+    const float sc = is_max ? 1.f : 1.f / (float)(kh * kw);
+    uint4 o;
+    __half2* op = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) op[j] = __floats2half2_rn(acc[2 * j] * sc, acc[2 * j + 1] * sc);
+    dst[i] = o;
+  }
+}
+
+int pool2d_f16_launch(const __half* src, __half* dst, int NI, int H, int W, int C, int kh, int kw,
+                      int sh, int sw, int ph, int pw, int is_max, cudaStream_t stream) {
+  if (C % 8) {
+    set_error("pool2d_f16: C must be a multiple of 8");
+    return -1;
+  }
+  const int Ho = (H + 2 * ph - kh) / sh + 1, Wo = (W + 2 * pw - kw) / sw + 1;
+  const size_t total = (size_t)NI * Ho * Wo * (C / 8);
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  note("pool2d_f16", 0.0, (double)total * 16.0 * (kh * kw + 1));
+  DFB_CUDA_OK(launch_pdl(pool2d_f16_kernel, dim3(blocks), dim3(256), 0, stream,
+                         reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), NI, H, W, C / 8,
+                         kh, kw, sh, sw, ph, pw, Ho, Wo, is_max));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // One DDIM step's arithmetic (reference ddim.py:241-245 CFG, :377-380 classifier term, :258-273
 // update), same operation order as the reference and no FMA contraction so the sampler arithmetic
 // itself is bit-compatible with the fp32 host path:

@@ -52,6 +52,7 @@ struct IGemmKParams {
   int ld_rowvec;
   int rows_per_sample;
   const float* residual;
+  const __half* residual_f16;
   int ld_res;
   int act;
   int splits;  // == cluster size along z (<= 8): the CTAs of one output tile reduce through DSMEM
@@ -96,6 +97,19 @@ __device__ __forceinline__ void epilogue16(const IGemmKParams& p, float (&v)[16]
     for (int j = 0; j < 4; ++j) {
       const float4 t = rs[j];
       v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+    }
+  }
+  if (p.residual_f16 != nullptr) {
+    const uint4* rs = reinterpret_cast<const uint4*>(p.residual_f16 + m * p.ld_res + n_base);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint4 u = rs[j];
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&u.z));
+      const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&u.w));
+      v[8 * j] += a.x; v[8 * j + 1] += a.y; v[8 * j + 2] += b.x; v[8 * j + 3] += b.y;
+      v[8 * j + 4] += c.x; v[8 * j + 5] += c.y; v[8 * j + 6] += d.x; v[8 * j + 7] += d.y;
     }
   }
   if (p.act == ACT_SILU) {
@@ -436,6 +450,30 @@ IGemmGeom gemm_geom(int M, int K) {
   return g;
 }
 
+IGemmGeom conv_taps_geom(int B, int T, int H, int W, int C, int kt, int kh, int kw) {
+  IGemmGeom g;
+  memset(&g, 0, sizeof(g));
+  g.B = B; g.T = T; g.H = H; g.W = W; g.C = C;
+  // 128 output positions per tile, filled W-first; each box extent divides 128
+  int rem = 128;
+  auto take = [&](int extent) {
+    int b = std::min(extent, rem);
+    while (rem % b) --b;
+    rem /= b;
+    return b;
+  };
+  g.bw = take(W); g.bh = take(H); g.bt = take(T); g.bb = rem;
+  g.ntaps = 0;
+  for (int a = 0; a < kt; ++a)
+    for (int b = 0; b < kh; ++b)
+      for (int c = 0; c < kw; ++c) {
+        g.dt[g.ntaps] = (int8_t)(a - kt / 2); g.dh[g.ntaps] = (int8_t)(b - kh / 2);
+        g.dw[g.ntaps] = (int8_t)(c - kw / 2);
+        ++g.ntaps;
+      }
+  return g;
+}
+
 IGemmGeom conv3x3_geom(int B, int H, int W, int C) {
   IGemmGeom g;
   memset(&g, 0, sizeof(g));
@@ -532,7 +570,7 @@ int igemm_plan(IGemmPlan* plan, const __half* A, const __half* Wt, int N, const 
   plan->ws = nullptr;
   plan->counters = nullptr;
   (void)ws; (void)ws_bytes; (void)counters; (void)ncounters;  // split-K no longer needs global scratch
-  if ((e.out_f16 && (e.ldo % 8)) || (e.out_f32 && (e.ldo % 4)) || (e.residual && (e.ld_res % 4)) ||
+  if ((e.out_f16 && (e.ldo % 8)) || (e.out_f32 && (e.ldo % 4)) || (e.residual && (e.ld_res % 4)) || (e.residual_f16 && (e.ld_res % 8)) ||
       (N % 16) != 0) {
     set_error("igemm: N must be a multiple of 16 and output/residual row strides 16-byte aligned");
     return -1;
@@ -614,7 +652,8 @@ int igemm_launch(const IGemmPlan& plan, cudaStream_t stream) {
   kp.out_f32 = plan.e.out_f32; kp.out_f16 = plan.e.out_f16; kp.ldo = plan.e.ldo;
   kp.bias = plan.e.bias; kp.rowvec = plan.e.rowvec; kp.ld_rowvec = plan.e.ld_rowvec;
   kp.rows_per_sample = plan.e.rows_per_sample;
-  kp.residual = plan.e.residual; kp.ld_res = plan.e.ld_res; kp.act = plan.e.act;
+  kp.residual = plan.e.residual; kp.residual_f16 = plan.e.residual_f16; kp.ld_res = plan.e.ld_res;
+  kp.act = plan.e.act;
   kp.splits = plan.splits;
   {
     const double out_b = (plan.e.out_f32 ? 4.0 : 0.0) + (plan.e.out_f16 ? 2.0 : 0.0);

@@ -123,6 +123,21 @@ int dfb_gemm(const void* a_f16_dev, const void* w_f16_dev, int M, int N, int K, 
 int dfb_conv3x3(const void* a_f16_dev, const void* w_f16_dev, int B, int H, int W, int C, int N,
                 const float* bias_dev, const float* rowvec_dev, const float* residual_dev, int act,
                 float* out_f32_dev, void* out_f16_dev, int splits, void* stream);
+/* "same"-padded stride-1 convolution with an odd (kt,kh,kw) kernel, kt*kh*kw <= 9, over fp16
+ * channels-last [B,T,H,W,C] as implicit GEMM (one TMA box per tap); w: fp16 [N, taps*C] with
+ * k = ((it*kh + ih)*kw + iw)*C + c.  Covers the CAVP encoders' (1,1,1), (1,3,3), (3,1,1) Conv3d and 3x3
+ * Conv2d with BatchNorm folded into w / bias (inference/model/cavp_modules.py:243-293, 1440-1483);
+ * residual_f16: optional fp16 [B,T,H,W,N] identity path, added before the activation. */
+int dfb_conv_taps(const void* a_f16_dev, const void* w_f16_dev, int B, int T, int H, int W, int C, int N,
+                  int kt, int kh, int kw, const float* bias_dev, const void* residual_f16_dev, int act,
+                  float* out_f32_dev, void* out_f16_dev, int splits, void* stream);
+/* im2col on fp16 channels-last images [NI,H,W,C] -> [NI*Ho*Wo, Kpad] (k = (ky*kw+kx)*C + c, zero padded
+ * to Kpad): strided / large-kernel convs (7x7 stem, stride-2 3x3 and 1x1) become plain GEMMs. */
+int dfb_im2col_f16(const void* src_dev, void* dst_dev, int NI, int H, int W, int C, int kh, int kw,
+                   int stride, int pad, int Kpad, void* stream);
+/* max (is_max=1) or average pooling on fp16 channels-last images */
+int dfb_pool2d_f16(const void* src_dev, void* dst_dev, int NI, int H, int W, int C, int kh, int kw, int sh,
+                   int sw, int ph, int pw, int is_max, void* stream);
 /* GroupNorm(32) (+SiLU) over concat(src0, src1) channels-last fp32 -> fp16 (util.py:214-216) */
 int dfb_groupnorm(const float* src0_dev, int C0, const float* src1_dev, int C1, int B, int HW,
                   const float* gamma_dev, const float* beta_dev, float eps, int silu, void* out_f16_dev,

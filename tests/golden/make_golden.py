@@ -250,3 +250,35 @@ def gen_vae_decode(name="vae_decode", seed=21):
 
 if __name__ == "__main__" and (len(sys.argv) < 2 or sys.argv[1] in ("all", "vae")):
     gen_vae_decode()
+
+
+def gen_cavp(name, seed, B, T, HW, spec_T):
+    """CAVP_Inference.encode_video / encode_spec (inference/model/cavp_model.py:47-84) through the mmcv
+    import shim, seeded weights incl. randomised BatchNorm statistics.  Inputs are regenerated from the
+    seed by the tests (a 224x224x32 clip is 19 MB), only the outputs are stored."""
+    t0 = time.time()
+    sys.path.insert(0, os.path.join(REF, "inference"))
+    from model.cavp_model import CAVP_Inference
+    from oracle import cavp_oracle
+    m = CAVP_Inference("Slowonly_pool", "cnn14_pool", 512).eval()
+    sd = cavp_oracle.seeded_state_dict(seed)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all("num_batches_tracked" in k or k == "logit_scale" for k in missing), (missing, unexpected)
+    g = torch.Generator().manual_seed(seed + 77)
+    video = torch.rand(B, T, 3, HW, HW, generator=g)
+    spec = torch.randn(B, 128, spec_T, generator=g)
+    with torch.no_grad():
+        v = m.encode_video(video, normalize=True, pool=False)
+        v_raw = m.encode_video(video, normalize=False, pool=False)
+        s = m.encode_spec(spec, normalize=True, pool=False)
+        s_raw = m.encode_spec(spec, normalize=False, pool=False)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), video_feat=v.numpy(), video_raw=v_raw.numpy(),
+                        spec_feat=s.numpy(), spec_raw=s_raw.numpy(), seed=np.int64(seed),
+                        shape=np.asarray([B, T, HW, spec_T]))
+    print(f"{name}: video {tuple(v.shape)} raw rms {float(v_raw.pow(2).mean().sqrt()):.3f}  spec {tuple(s.shape)} "
+          f"raw rms {float(s_raw.pow(2).mean().sqrt()):.3f} ({time.time() - t0:.1f}s)")
+
+
+if __name__ == "__main__" and (len(sys.argv) < 2 or sys.argv[1] in ("all", "cavp")):
+    gen_cavp("cavp_small", 31, 2, 4, 64, 64)
+    gen_cavp("cavp_full", 32, 1, 32, 224, 512)

@@ -147,3 +147,32 @@ def test_vae_decode_oracle_matches_reference():
     img = vae_oracle.decode_first_stage(sd, torch.from_numpy(g["z"]))
     assert img.shape == (1, 3, 128, 512)
     assert rel_l2(img[:, 0], g["mel"]) < 1e-5
+
+
+# ------------------------------------------------------------------------- CAVP encoders (a17, a18)
+def cavp_inputs(g):
+    B, T, HW, spec_T = (int(v) for v in g["shape"])
+    gen = torch.Generator().manual_seed(int(g["seed"]) + 77)
+    video = torch.rand(B, T, 3, HW, HW, generator=gen)
+    spec = torch.randn(B, 128, spec_T, generator=gen)
+    return video, spec
+
+
+def test_cavp_oracle_matches_reference():
+    from oracle import cavp_oracle
+    g = load("cavp_small")
+    sd = cavp_oracle.seeded_state_dict(int(g["seed"]))
+    video, spec = cavp_inputs(g)
+    assert rel_l2(cavp_oracle.encode_video(sd, video, normalize=False, pool=False), g["video_raw"]) < 1e-5
+    assert rel_l2(cavp_oracle.encode_video(sd, video, normalize=True, pool=False), g["video_feat"]) < 1e-5
+    assert rel_l2(cavp_oracle.encode_spec(sd, spec, normalize=False, pool=False), g["spec_raw"]) < 1e-5
+    assert rel_l2(cavp_oracle.encode_spec(sd, spec, normalize=True, pool=False), g["spec_feat"]) < 1e-5
+
+
+def test_cavp_module_keys_match_reference():
+    from diff_foley_b200.cavp import CAVPInferenceB200
+    from oracle import cavp_oracle
+    with torch.device("meta"):
+        m = CAVPInferenceB200()
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items() if "num_batches" not in k and k != "logit_scale"}
+    assert got == dict(cavp_oracle.cavp_param_shapes())
