@@ -293,6 +293,71 @@ def run_ours(args):
     return line
 
 
+def run_cavp(args):
+    """BASELINE config 5: CAVP video (32 frames, 224x224) + audio (128x512 mel) encoder forward,
+    data-parallel over the ranks (no collective on the path).  Reported as clips/s; not the headline
+    metric -- `python bench.py --workload cavp --clips-per-gpu 8`."""
+    import torch
+    import torch.distributed as dist
+    from diff_foley_b200.cavp import CAVPInferenceB200
+    from diff_foley_b200.weights import randomize_parameters_
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    m = CAVPInferenceB200().to(dev).eval()
+    g = torch.Generator(device=dev).manual_seed(3)
+    for n, p in m.named_parameters():
+        if p.dim() > 1:
+            p.data.copy_(torch.randn(p.shape, generator=g, device=dev) * (1.0 / p[0].numel()) ** 0.5)
+    for n, b in m.named_buffers():
+        if n.endswith("running_var"):
+            b.copy_(0.5 + torch.rand(b.shape, generator=g, device=dev))
+    C = args.clips_per_gpu
+    video = torch.rand(C, 32, 3, 224, 224, generator=g, device=dev)
+    spec = torch.randn(C, 128, 512, generator=g, device=dev)
+
+    def step():
+        m.encode_video(video, normalize=True, pool=False)
+        m.encode_spec(spec, normalize=True, pool=False)
+
+    K, W = max(1, args.steps), max(3, args.warmup)
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m.launches = 0
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(ms.item())
+        gflop = 382.99  # per clip: 333.99 video + 49.00 audio (SURVEY 6)
+        pk = peaks()
+        val = C * world * K / (ms / 1e3)
+        print(json.dumps({
+            "metric": "CAVP clips/sec (video 32x224x224 + audio 128x512)", "value": val, "unit": "clips/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
+            "config": {"workload": f"config 5: CAVP encode_video + encode_spec, {C} clips/GPU, data parallel"},
+            "gpu_launches": int(m.launches),
+            "roofline": {"bound": "tensor", "achieved": val / world * gflop / 1e3, "peak": pk["tf_sust"],
+                         "unit": "TFLOP/s", "frac": val / world * gflop / 1e3 / pk["tf_sust"], "traffic": None,
+                         "peak_source": pk["src"]}}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -301,8 +366,11 @@ def main():
     ap.add_argument("--clips-per-gpu", type=int, default=1)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="ddim", choices=["ddim", "cavp"])
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "cavp":
+        run_cavp(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
