@@ -552,11 +552,11 @@ int igemm_plan(IGemmPlan* plan, const __half* A, const __half* Wt, int N, const 
         const int kb_cta = (kb_total + sp - 1) / sp;
         const double stage_kb = (rows_per_tile + bn) * 128.0 / 1024.0;
         const double waves = std::ceil((double)tiles * sp / nsm);
-        // per-CTA fill at ~55 KB/us, but the whole grid cannot pull more than ~3.3 GB/ms through
+        // per-CTA fill at ~55 KB/us, but the whole grid cannot pull more than ~3.3-4 GB/ms through
         // L2 (measured: tools/microbench_deep.py) -- the N-tile CTAs of a k-block all re-read the
         // same A lines, so narrower tiles / more CTAs do not help once that limit is reached
         const double t_cta = waves * kb_cta * stage_kb / 55.0;
-        const double t_grid = (double)tiles * sp * kb_cta * stage_kb / 3300.0;
+        const double t_grid = (double)tiles * sp * kb_cta * stage_kb / 4000.0;
         const double t = std::max(t_cta, t_grid) + (sp > 1 ? 1.0 : 0.0) + 0.05 * (bn / 16) * waves + 3.0;
         if (t < best - 1e-9) { best = t; best_bn = bn; best_s = sp; }
       }

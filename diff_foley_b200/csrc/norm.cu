@@ -32,66 +32,93 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 constexpr int GN_THREADS = 512;
+constexpr int GN_MAXP = 8;   // float2 pairs held per thread
 
-// grid = (32 groups, B).  The group's [HW x cpg] slab is staged in shared memory once.
+// grid = (P, 32 groups, B) with cluster dims (P,1,1): the P CTAs of a cluster share one (sample,
+// group) slab, split along the pixel axis.  Each thread keeps its <= 8 channel pairs in registers (one
+// global read, no shared-memory slab); the group statistics are two-pass (mean, then centred second
+// moment, like ATen) with the per-CTA partials exchanged through distributed shared memory.
 __global__ void __launch_bounds__(GN_THREADS)
 groupnorm_kernel(const float* __restrict__ src0, int C0, const float* __restrict__ src1, int C1,
                  int HW, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float eps, int silu, __half* __restrict__ out, __half* __restrict__ raw_out) {
-  extern __shared__ float slab[];  // [HW][cpg]
   __shared__ float red[GN_THREADS / 32];
+  __shared__ float part[2];  // this CTA's partial sum / partial centred sum of squares
   pdl_wait();
   pdl_launch_dependents();
+  const int P = gridDim.x, rank = blockIdx.x;
   const int C = C0 + C1;
   const int cpg = C / 32;
   const int hp = cpg >> 1;  // channel pairs per pixel
-  const int g = blockIdx.x, b = blockIdx.y;
+  const int g = blockIdx.y, b = blockIdx.z;
   const int cbase = g * cpg;
-  const int npairs = HW * hp;
+  const int px_per = (HW + P - 1) / P;
+  const int px0 = rank * px_per;
+  const int npx = max(0, min(px_per, HW - px0));
+  const int npairs = npx * hp;
 
+  float2 v[GN_MAXP];
   float s = 0.f;
-  for (int i = threadIdx.x; i < npairs; i += GN_THREADS) {
-    const int px = i / hp;
-    const int c = cbase + 2 * (i - px * hp);
-    float2 v;
-    if (c < C0)
-      v = *reinterpret_cast<const float2*>(src0 + ((size_t)b * HW + px) * C0 + c);
-    else
-      v = *reinterpret_cast<const float2*>(src1 + ((size_t)b * HW + px) * C1 + (c - C0));
-    reinterpret_cast<float2*>(slab)[i] = v;
-    s += v.x + v.y;
+#pragma unroll
+  for (int k = 0; k < GN_MAXP; ++k) {
+    const int i = threadIdx.x + k * GN_THREADS;
+    v[k] = make_float2(0.f, 0.f);
+    if (i < npairs) {
+      const int px = px0 + i / hp;
+      const int c = cbase + 2 * (i % hp);
+      v[k] = (c < C0) ? *reinterpret_cast<const float2*>(src0 + ((size_t)b * HW + px) * C0 + c)
+                      : *reinterpret_cast<const float2*>(src1 + ((size_t)b * HW + px) * C1 + (c - C0));
+      s += v[k].x + v[k].y;
+    }
   }
   const float inv_n = 1.f / (float)(HW * cpg);
-  const float mean = block_sum<GN_THREADS>(s, red) * inv_n;
-  float q = 0.f;
-  for (int i = threadIdx.x; i < npairs; i += GN_THREADS) {
-    const float2 v = reinterpret_cast<const float2*>(slab)[i];
-    const float dx = v.x - mean, dy = v.y - mean;
-    q += dx * dx + dy * dy;
-  }
-  const float var = block_sum<GN_THREADS>(q, red) * inv_n;
-  const float rstd = rsqrtf(var + eps);
-  for (int i = threadIdx.x; i < npairs; i += GN_THREADS) {
-    const int px = i / hp;
-    const int c = cbase + 2 * (i - px * hp);
-    const float2 v = reinterpret_cast<const float2*>(slab)[i];
-    float y0 = (v.x - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-    float y1 = (v.y - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
-    if (silu) {
-      y0 = y0 / (1.f + expf(-y0));
-      y1 = y1 / (1.f + expf(-y1));
+  auto cluster_total = [&](float local, int slot) -> float {
+    const float t = block_sum<GN_THREADS>(local, red);
+    if (P == 1) return t;
+    if (threadIdx.x == 0) part[slot] = t;
+    cluster_sync_all();
+    float tot = 0.f;
+    const uint32_t a = smem_u32(&part[slot]);
+    for (int r = 0; r < P; ++r) {
+      float x;
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(x) : "r"(mapa_shared(a, (uint32_t)r)) : "memory");
+      tot += x;
     }
-    const size_t o = ((size_t)b * HW + px) * C + c;
-    *reinterpret_cast<__half2*>(out + o) = __floats2half2_rn(y0, y1);
-    if (raw_out != nullptr) *reinterpret_cast<__half2*>(raw_out + o) = __floats2half2_rn(v.x, v.y);
+    return tot;
+  };
+  const float mean = cluster_total(s, 0) * inv_n;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < GN_MAXP; ++k) {
+    const int i = threadIdx.x + k * GN_THREADS;
+    if (i < npairs) {
+      const float dx = v[k].x - mean, dy = v[k].y - mean;
+      q += dx * dx + dy * dy;
+    }
   }
+  const float var = cluster_total(q, 1) * inv_n;
+  const float rstd = rsqrtf(var + eps);
+#pragma unroll
+  for (int k = 0; k < GN_MAXP; ++k) {
+    const int i = threadIdx.x + k * GN_THREADS;
+    if (i < npairs) {
+      const int px = px0 + i / hp;
+      const int c = cbase + 2 * (i % hp);
+      float y0 = (v[k].x - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+      float y1 = (v[k].y - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
+      if (silu) {
+        y0 = y0 / (1.f + expf(-y0));
+        y1 = y1 / (1.f + expf(-y1));
+      }
+      const size_t o = ((size_t)b * HW + px) * C + c;
+      *reinterpret_cast<__half2*>(out + o) = __floats2half2_rn(y0, y1);
+      if (raw_out != nullptr) *reinterpret_cast<__half2*>(raw_out + o) = __floats2half2_rn(v[k].x, v[k].y);
+    }
+  }
+  if (P > 1) cluster_sync_all();  // peers may still be reading part[] of this CTA
 }
 
-int norm_init() {
-  DFB_CUDA_OK(cudaFuncSetAttribute(groupnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   200 * 1024));
-  return 0;
-}
+int norm_init() { return 0; }
 
 int groupnorm_launch(const float* src0, int C0, const float* src1, int C1, int B, int HW,
                      const float* gamma, const float* beta, float eps, int silu, __half* out,
@@ -102,66 +129,99 @@ int groupnorm_launch(const float* src0, int C0, const float* src1, int C1, int B
     set_error("groupnorm: channels must be a multiple of 64 (32 groups of an even width)");
     return -1;
   }
-  const size_t smem = (size_t)HW * (C / 32) * sizeof(float);
-  if (smem > 200 * 1024) {
-    set_error("groupnorm: group slab of " + std::to_string(smem) + " bytes exceeds shared memory");
+  const long pairs = (long)HW * (C / 64);
+  const long cap = (long)GN_THREADS * GN_MAXP;
+  int P = (int)((pairs + cap - 1) / cap);
+  // spread a slab over a few SMs when there are enough pixels to split (latency, not capacity)
+  if (HW >= 1024) P = std::max(P, 4); else if (HW >= 256) P = std::max(P, 2);
+  if (P > 8) {
+    set_error("groupnorm: group slab of " + std::to_string(pairs * 2) + " elements is too large");
     return -1;
   }
-  note("groupnorm", 0.0, (double)B * HW * C * (4.0 + 2.0 + (raw_out ? 2.0 : 0.0)), B * HW, C, 0, 1, 32 * B);
-  DFB_CUDA_OK(launch_pdl(groupnorm_kernel, dim3(dim3(32, B)), dim3(GN_THREADS), smem, stream, src0, C0, src1, C1, HW, gamma, beta,
-                                                              eps, silu, out, raw_out));
-  DFB_CUDA_OK(cudaGetLastError());
+  note("groupnorm", 0.0, (double)B * HW * C * (4.0 + 2.0 + (raw_out ? 2.0 : 0.0)), B * HW, C, 0, 1, 32 * B * P);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(P, 32, B);
+  cfg.blockDim = dim3(GN_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = P;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  DFB_CUDA_OK(cudaLaunchKernelEx(&cfg, groupnorm_kernel, src0, C0, src1, C1, HW, gamma, beta, eps, silu, out,
+                                 raw_out));
   return 0;
 }
 
-// One warp per row of fp32 [rows, C]; three L1-resident passes (mean, centred variance, write).
-__global__ void __launch_bounds__(256)
+// One warp per row of fp32 [rows, C].  The row lives in registers (<= 10 float4 per lane, C <= 1280):
+// one global read, two-pass statistics on the registers, fp16 write.  4 warps per CTA so that even the
+// 128-row deep levels spread over 32 SMs.
+constexpr int LN_WARPS = 4;
+constexpr int LN_MAXV = 10;
+__global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_kernel(const float* __restrict__ src, int rows, int C, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __half* __restrict__ out) {
   pdl_wait();
   pdl_launch_dependents();
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float4* x = reinterpret_cast<const float4*>(src + (size_t)row * C);
   const int n4 = C >> 2;
+  float4 v[LN_MAXV];
   float s = 0.f;
-  for (int i = lane; i < n4; i += 32) {
-    const float4 v = x[i];
-    s += (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k) {
+    const int i = lane + 32 * k;
+    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n4) {
+      v[k] = x[i];
+      s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
   }
   const float mean = warp_sum(s) / (float)C;
   float q = 0.f;
-  for (int i = lane; i < n4; i += 32) {
-    const float4 v = x[i];
-    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
-    q += (a * a + b * b) + (c * c + d * d);
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k) {
+    if (lane + 32 * k < n4) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
   }
   const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
   __half* o = out + (size_t)row * C;
-  for (int i = lane; i < n4; i += 32) {
-    const float4 v = x[i];
-    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i);
-    const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + i);
-    const __half2 h0 = __floats2half2_rn((v.x - mean) * rstd * gm.x + bt.x,
-                                         (v.y - mean) * rstd * gm.y + bt.y);
-    const __half2 h1 = __floats2half2_rn((v.z - mean) * rstd * gm.z + bt.z,
-                                         (v.w - mean) * rstd * gm.w + bt.w);
-    uint2 u;
-    u.x = *reinterpret_cast<const uint32_t*>(&h0);
-    u.y = *reinterpret_cast<const uint32_t*>(&h1);
-    *reinterpret_cast<uint2*>(o + 4 * i) = u;
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k) {
+    const int i = lane + 32 * k;
+    if (i < n4) {
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+      const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + i);
+      const __half2 h0 = __floats2half2_rn((v[k].x - mean) * rstd * gm.x + bt.x,
+                                           (v[k].y - mean) * rstd * gm.y + bt.y);
+      const __half2 h1 = __floats2half2_rn((v[k].z - mean) * rstd * gm.z + bt.z,
+                                           (v[k].w - mean) * rstd * gm.w + bt.w);
+      uint2 u;
+      u.x = *reinterpret_cast<const uint32_t*>(&h0);
+      u.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(o + 4 * i) = u;
+    }
   }
 }
 
 int layernorm_launch(const float* src, int rows, int C, const float* gamma, const float* beta,
                      float eps, __half* out, cudaStream_t stream) {
-  if (C % 4 != 0) {
-    set_error("layernorm: C must be a multiple of 4");
+  if (C % 4 != 0 || C > 128 * LN_MAXV) {
+    set_error("layernorm: C must be a multiple of 4 and <= 1280");
     return -1;
   }
-  note("layernorm", 0.0, (double)rows * C * 6.0, rows, C, 0, 1, (rows + 7) / 8);
-  DFB_CUDA_OK(launch_pdl(layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, src, rows, C, gamma, beta, eps, out));
+  const int nblk = (rows + LN_WARPS - 1) / LN_WARPS;
+  note("layernorm", 0.0, (double)rows * C * 6.0, rows, C, 0, 1, nblk);
+  DFB_CUDA_OK(launch_pdl(layernorm_kernel, dim3(nblk), dim3(LN_WARPS * 32), 0, stream, src, rows, C, gamma, beta, eps, out));
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
 }
