@@ -162,8 +162,10 @@ __device__ __forceinline__ void epilogue16_geglu(const IGemmKParams& p, const fl
   }
 }
 
+// STAGES-deep operand ring; the shallow-ring instantiations (<=3-4 stages, ~97 KB) let two CTAs share
+// an SM so one CTA's epilogue overlaps the other's main loop -- used for short-K problems.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(IGEMM_THREADS, 1)
+__global__ void __launch_bounds__(IGEMM_THREADS, (STAGES <= 4) ? 2 : 1)
 igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                      const __grid_constant__ CUtensorMap tmW,
                      const __grid_constant__ IGemmKParams p) {
@@ -606,6 +608,12 @@ int igemm_plan(IGemmPlan* plan, const __half* A, const __half* Wt, int N, const 
 }
 
 int igemm_init() {
+  DFB_CUDA_OK(cudaFuncSetAttribute(igemm_tcgen05_kernel<64, 4>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   IGemmSmem<64, 4>::DYN_BYTES));
+  DFB_CUDA_OK(cudaFuncSetAttribute(igemm_tcgen05_kernel<128, 3>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   IGemmSmem<128, 3>::DYN_BYTES));
   DFB_CUDA_OK(cudaFuncSetAttribute(igemm_tcgen05_kernel<64, 8>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    IGemmSmem<64, 8>::DYN_BYTES));
@@ -662,8 +670,11 @@ int igemm_launch(const IGemmPlan& plan, cudaStream_t stream) {
              (plan.e.residual ? 4.0 * plan.M * plan.e.ldo : 0.0),
          plan.M, plan.N, plan.K, plan.splits, plan.tiles_m * plan.tiles_n * plan.splits);
   }
-  if (plan.BN == 64) return launch_t<64, 8>(plan, kp, stream);
-  return launch_t<128, 6>(plan, kp, stream);
+  // short K loops: shallow ring, two CTAs per SM (epilogue of one overlaps the main loop of the other)
+  const int kb_cta = (g.ntaps * (g.C / BLOCK_K) + plan.splits - 1) / plan.splits;
+  const bool shallow = kb_cta <= 8 && plan.tiles_m * plan.tiles_n * plan.splits > num_sms();
+  if (plan.BN == 64) return shallow ? launch_t<64, 4>(plan, kp, stream) : launch_t<64, 8>(plan, kp, stream);
+  return shallow ? launch_t<128, 3>(plan, kp, stream) : launch_t<128, 6>(plan, kp, stream);
 }
 
 }  // namespace dfb
