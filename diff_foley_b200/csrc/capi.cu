@@ -24,6 +24,7 @@ int kernels_init() {
     rc = igemm_init();
     if (!rc) rc = norm_init();
     if (!rc) rc = attention_init();
+    if (!rc) rc = elementwise_init();
   });
   return rc;
 }

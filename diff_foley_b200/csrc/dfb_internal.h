@@ -62,6 +62,7 @@ int kernels_init();
 int igemm_init();
 int norm_init();
 int attention_init();
+int elementwise_init();
 
 // ------------------------------------------------------------------- implicit-GEMM (tcgen05)
 // One kernel covers Linear, 1x1 conv, 3x3 conv (9 shifted TMA boxes, zero-filled halo) and the

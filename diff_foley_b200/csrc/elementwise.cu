@@ -370,4 +370,20 @@ int ddim_update_launch(const float* x, const float* eps_uncond, const float* eps
   return 0;
 }
 
+int elementwise_init() {
+#define DFB_MAXSHARED(k) \
+  DFB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
+  DFB_MAXSHARED(temb_kernel);
+  DFB_MAXSHARED(cast_f16_kernel);
+  DFB_MAXSHARED(upsample2x_f16_kernel);
+  DFB_MAXSHARED(im2col_s2_kernel);
+  DFB_MAXSHARED(stem_conv_kernel);
+  DFB_MAXSHARED(head_conv_kernel);
+  DFB_MAXSHARED(im2col_f16_kernel);
+  DFB_MAXSHARED(pool2d_f16_kernel);
+  DFB_MAXSHARED(ddim_update_kernel);
+#undef DFB_MAXSHARED
+  return 0;
+}
+
 }  // namespace dfb

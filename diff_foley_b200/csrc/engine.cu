@@ -985,6 +985,10 @@ int dfb_unet_create(const dfb_unet_cfg* cfg, int device, dfb_handle* out) {
     int rk = kernels_init();
     if (rk) return rk;
   }
+  for (const void* k : {(const void*)step_begin_kernel, (const void*)step_end_kernel,
+                        (const void*)ddim_update_graph_kernel})
+    DFB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
   dfb_unet* e = new dfb_unet();
   e->cfg = *cfg;
   e->device = device;

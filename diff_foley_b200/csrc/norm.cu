@@ -118,7 +118,6 @@ groupnorm_kernel(const float* __restrict__ src0, int C0, const float* __restrict
   if (P > 1) cluster_sync_all();  // peers may still be reading part[] of this CTA
 }
 
-int norm_init() { return 0; }
 
 int groupnorm_launch(const float* src0, int C0, const float* src1, int C1, int B, int HW,
                      const float* gamma, const float* beta, float eps, int silu, __half* out,
@@ -223,6 +222,17 @@ int layernorm_launch(const float* src, int rows, int C, const float* gamma, cons
   note("layernorm", 0.0, (double)rows * C * 6.0, rows, C, 0, 1, nblk);
   DFB_CUDA_OK(launch_pdl(layernorm_kernel, dim3(nblk), dim3(LN_WARPS * 32), 0, stream, src, rows, C, gamma, beta, eps, out));
   DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// All kernels of the plan ask for the same (maximum-shared) L1/shared-memory split: the GEMM and
+// attention kernels need ~200 KB of shared memory, and an SM has to drain to change its carve-out, so a
+// small-smem kernel with the default preference between two GEMMs would force two reconfigurations.
+int norm_init() {
+  DFB_CUDA_OK(cudaFuncSetAttribute(groupnorm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
+  DFB_CUDA_OK(cudaFuncSetAttribute(layernorm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
   return 0;
 }
 
