@@ -102,6 +102,10 @@ struct IGemmPlan {
   int tiles_m, tiles_n, splits;
   float* ws;         // split-K workspace (tiles*splits*128*BN floats) or nullptr when splits==1
   int* counters;     // per-tile arrival counters (zero-initialised, self-resetting)
+  // weights of the NEXT GEMM of the plan: every CTA issues an L2 prefetch for a slice of them, so the
+  // next (weight-streaming) kernel finds its operand in L2 instead of waiting on cold HBM misses
+  const void* next_w = nullptr;
+  size_t next_w_bytes = 0;
 };
 
 // Builds tensor maps + tiling for `A` (fp16 [B,T,H,W,C]) and `Wt` (fp16 [N, ntaps*C]).

@@ -520,6 +520,10 @@ struct Builder {
   __half* a16[3] = {nullptr, nullptr, nullptr};
   float* t32[3] = {nullptr, nullptr, nullptr};
   int rc = 0;
+  std::shared_ptr<IGemmPlan> prev_gemm;
+  // cross-layer L2 prefetch of the next GEMM's weights: measured neutral-to-slightly-negative on B200
+  // (the deep layers are fill-rate-, not HBM-latency-bound), so it is opt-in: DFB_L2_PREFETCH=1
+  bool no_prefetch = (getenv("DFB_L2_PREFETCH") == nullptr);
 
   void use16(size_t n) { need16 = std::max(need16, n); }
   void use32(size_t n) { need32 = std::max(need32, n); }
@@ -549,7 +553,14 @@ struct Builder {
     }
     int r = igemm_plan(&ip, A, lin.w, lin.N, g, ep, 0, e->ws, e->ws_bytes, e->counters, e->ncounters);
     if (r) { rc = r; return; }
-    plan->ops.push_back([ip](cudaStream_t s) { return igemm_launch(ip, s); });
+    auto sp = std::make_shared<IGemmPlan>(ip);
+    // link the previous GEMM to this one's weights (L2 prefetch of the next layer, see igemm kernel)
+    if (prev_gemm && (size_t)lin.N * ip.K * 2 >= ((size_t)1 << 20) && !no_prefetch) {
+      prev_gemm->next_w = lin.w;
+      prev_gemm->next_w_bytes = (size_t)lin.N * ip.K * 2;
+    }
+    prev_gemm = sp;
+    plan->ops.push_back([sp](cudaStream_t s) { return igemm_launch(*sp, s); });
   }
   void op(std::function<int(cudaStream_t)> f) {
     if (rc || dry) return;

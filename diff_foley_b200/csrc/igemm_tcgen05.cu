@@ -56,6 +56,8 @@ struct IGemmKParams {
   int ld_res;
   int act;
   int splits;  // == cluster size along z (<= 8): the CTAs of one output tile reduce through DSMEM
+  const uint8_t* next_w;  // optional: weights of the next GEMM, prefetched into L2 slice-wise
+  unsigned long long next_w_bytes;
 };
 
 template <int BN, int STAGES>
@@ -283,6 +285,20 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     const int sub = warp & 3;          // TMEM sub-partition this warp may read
     const int r = sub * 32 + lane;     // accumulator row (= TMEM lane) owned by this thread
     const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
+    if (warp == 2 && lane == 0 && p.next_w != nullptr) {
+      // (an epilogue warp: idle until the accumulator is complete, and not on the TMA/MMA critical path)
+      // software pipelining across layers: pull this CTA's slice of the next GEMM's weights into L2
+      const unsigned long long nct = (unsigned long long)gridDim.x * gridDim.y * gridDim.z;
+      const unsigned long long cta = ((unsigned long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      const unsigned long long per = ((p.next_w_bytes + nct - 1) / nct + 4095ull) & ~4095ull;
+      unsigned long long off = cta * per;
+      const unsigned long long end = min(off + per, p.next_w_bytes & ~15ull);
+      for (; off < end; off += 4096ull) {
+        const unsigned int sz = (unsigned int)min(4096ull, end - off);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.next_w + off), "r"(sz) : "memory");
+      }
+    }
+    __syncwarp();
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (!split) {
@@ -663,6 +679,8 @@ int igemm_launch(const IGemmPlan& plan, cudaStream_t stream) {
   kp.residual = plan.e.residual; kp.residual_f16 = plan.e.residual_f16; kp.ld_res = plan.e.ld_res;
   kp.act = plan.e.act;
   kp.splits = plan.splits;
+  kp.next_w = reinterpret_cast<const uint8_t*>(plan.next_w);
+  kp.next_w_bytes = plan.next_w_bytes;
   {
     const double out_b = (plan.e.out_f32 ? 4.0 : 0.0) + (plan.e.out_f16 ? 2.0 : 0.0);
     note(g.ntaps == 9 ? "igemm_conv3x3" : "igemm_linear", 2.0 * plan.M * plan.N * plan.K,
