@@ -197,21 +197,26 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   const int kb1 = (int)(((long)(blockIdx.z + 1) * kb_total) / p.splits);
   const int nkb = kb1 - kb0;
 
-  // ---- one-time setup
+  // ---- one-time setup.  Weights never depend on the preceding kernel, so the producer thread
+  // initialises the barriers itself and issues the weight (W) loads of the first ring of stages
+  // BEFORE the programmatic-dependent-launch wait: they stream from HBM while the predecessor is still
+  // finishing.  Only the activation (A) loads and the epilogue's reads wait for it.
+  const int npre = min(nkb, STAGES);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+    for (int i = 0; i < npre; ++i) {
+      mbar_expect_tx(&full_bar[i], L::STAGE_BYTES);
+      tma_load_2d(smem + i * L::STAGE_BYTES + L::A_BYTES, &tmW, &full_bar[i], (kb0 + i) * BLOCK_K, n0);
+    }
   }
   if (warp == 1) {
-    if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) {
-        mbar_init(&full_bar[s], 1);
-        mbar_init(&empty_bar[s], 1);
-      }
-      mbar_init(tmem_full_bar, 1);
-      fence_mbar_init();
-    }
-    __syncwarp();
     tmem_alloc(tmem_slot, BN);  // BN fp32 columns x 128 lanes (power of two >= 32)
     tmem_relinquish();
   }
@@ -244,16 +249,16 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     if (lane == 0) {
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
         const int kb = kb0 + i;
         const int tap = kb / p.kpt;
         const int c0 = (kb - tap * p.kpt) * BLOCK_K;
         uint8_t* sa = smem + s * L::STAGE_BYTES;
-        uint8_t* sw = sa + L::A_BYTES;
-        mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+        if (i >= npre) {  // ring slot reuse: wait for the MMAs that read it, then arm + load W as well
+          mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          tma_load_2d(sa + L::A_BYTES, &tmW, &full_bar[s], kb * BLOCK_K, n0);
+        }
         tma_load_5d(sa, &tmA, &full_bar[s], c0, x0 + p.dw[tap], y0 + p.dh[tap], t0 + p.dt[tap], b0);
-        tma_load_2d(sw, &tmW, &full_bar[s], kb * BLOCK_K, n0);
       }
     }
   } else if (warp == 1) {
