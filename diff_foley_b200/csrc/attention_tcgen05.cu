@@ -3,8 +3,9 @@
 //
 // One CTA owns a 128-query tile of one (sample, head).  Per block of KB keys:
 //   S = Q K^T        tcgen05.mma, fp16 operands from shared memory, fp32 S[128 x KB] in TMEM (double
-//                    buffered: S_{j+1} is issued while the softmax warps work on S_j)
-//   P = softmax-blk  4 warps, one query row per thread (row = TMEM lane, no shuffles): tcgen05.ld,
+//                    buffered: S_{j+1} is issued while the softmax warps work on S_j), KB <= 64
+//   P = softmax-blk  4 warps, one query row per thread (row = TMEM lane, no shuffles): ONE tcgen05.ld
+//                    pass pulls the thread's whole S row of the block into registers,
 //                    running max / sum in registers, exp2 with the d^-0.5 scale folded in, P written
 //                    as fp16 into shared memory in the MMA's canonical K-major layout
 //   O += P V         tcgen05.mma with V as an MN-major B operand (no transposed copy of V); O[128 x d]
@@ -42,7 +43,7 @@ constexpr int ATT_BM = 128;  // queries per CTA
 struct AttParams {
   __half* out;
   int ldo;
-  int heads, Lq, Lk, d, dpad, KB, nblocks;
+  int heads, Lq, Lk, d, dpad, KB, nblocks, tmem_cols;
   float scale_log2;  // d^-0.5 * log2(e)
   int swap_lbo;      // debug: swap LBO/SBO of the un-swizzled descriptors
 };
@@ -78,7 +79,12 @@ __host__ __device__ inline AttSmem att_smem_layout(int dpad, int KB) {
   return s;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+// Resources are sized so that two CTAs share an SM for head dims <= 128 (<= 97 KB of shared memory,
+// 256 TMEM columns): one CTA's softmax overlaps the other's tensor-core work and loads.
+// NQ = 16-column chunks of S per key block: 4 (KB <= 64; 2 CTAs/SM -- grids larger than the machine) or
+// 8 (KB <= 128; half as many softmax/MMA round trips per CTA -- small grids, latency-bound).
+template <int NQ>
+__global__ void __launch_bounds__(ATT_THREADS, (NQ <= 4) ? 2 : 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttParams p) {
   extern __shared__ uint8_t att_raw[];
@@ -117,7 +123,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -126,8 +132,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   pdl_wait();  // q/k/v come from the preceding GEMM
   pdl_launch_dependents();  // only after our own wait: at most two grids of the chain overlap
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_s[2] = {tmem_base, tmem_base + 128};
-  const uint32_t tm_o = tmem_base + 256;
+  const uint32_t tm_s[2] = {tmem_base, tmem_base + NQ * 16};  // S double buffer: 2 x (NQ*16 fp32 columns)
+  const uint32_t tm_o = tmem_base + 2 * NQ * 16;               // O: dpad fp32 columns
 
   if (warp == 0) {
     // ======================================================================== TMA producer
@@ -207,31 +213,73 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       mbar_wait(&s_full[s], (j >> 1) & 1);
       tc_fence_after();
       const int kvalid = min(KB, p.Lk - j * KB);  // keys of this block that exist
-      // ---- pass 1: row max
-      float mx = -INFINITY;
+      float mx, m_new, alpha, psum = 0.f;
+      uint8_t* prow = smem + L.off_p[s] + r * 16;
+      if constexpr (NQ <= 4) {
+      // ---- one TMEM pass: the whole S row of this block (KB <= 64 values) into registers
+      uint32_t raw[NQ][16];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+        if (q * 16 < KB) tmem_ld_32x16(tm_s[s] + lane_off + q * 16, raw[q]);
+      tmem_ld_wait();
+      mx = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+        if (q * 16 < KB) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (q * 16 + i < kvalid) mx = fmaxf(mx, __uint_as_float(raw[q][i]));
+        }
+      m_new = fmaxf(m_run, mx * p.scale_log2);
+      alpha = exp2f(m_run - m_new);  // 0 on the first block (m_run = -inf)
+      // ---- p = exp2(s*scale - m), row sum, fp16 P tile in the canonical K-major layout
+
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+        if (q * 16 < KB) {
+          float e[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float v = exp2f(fmaf(__uint_as_float(raw[q][i]), p.scale_log2, -m_new));
+            e[i] = (q * 16 + i < kvalid) ? v : 0.f;
+            psum += e[i];
+          }
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            __half2 h0 = __floats2half2_rn(e[8 * g + 0], e[8 * g + 1]);
+            __half2 h1 = __floats2half2_rn(e[8 * g + 2], e[8 * g + 3]);
+            __half2 h2 = __floats2half2_rn(e[8 * g + 4], e[8 * g + 5]);
+            __half2 h3 = __floats2half2_rn(e[8 * g + 6], e[8 * g + 7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(prow + (q * 2 + g) * (ATT_BM * 16)) = u;
+          }
+        }
+      } else {
+        // wide key blocks: two rolled TMEM passes (max, then exp) keep the code small -- this kernel
+        // starts with a cold instruction cache on every launch
+      mx = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < KB; c += 16) {
-        uint32_t raw[16];
-        tmem_ld_32x16(tm_s[s] + lane_off + c, raw);
+        uint32_t rw[16];
+        tmem_ld_32x16(tm_s[s] + lane_off + c, rw);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (c + i < kvalid) mx = fmaxf(mx, __uint_as_float(raw[i]));
+          if (c + i < kvalid) mx = fmaxf(mx, __uint_as_float(rw[i]));
       }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float alpha = exp2f(m_run - m_new);  // 0 on the first block (m_run = -inf)
-      // ---- pass 2: p = exp2(s*scale - m), row sum, fp16 P tile in the canonical K-major layout
-      uint8_t* prow = smem + L.off_p[s] + r * 16;
-      float psum = 0.f;
+      m_new = fmaxf(m_run, mx * p.scale_log2);
+      alpha = exp2f(m_run - m_new);  // 0 on the first block (m_run = -inf)
 #pragma unroll 1
       for (int c = 0; c < KB; c += 16) {
-        uint32_t raw[16];
-        tmem_ld_32x16(tm_s[s] + lane_off + c, raw);
+        uint32_t rw[16];
+        tmem_ld_32x16(tm_s[s] + lane_off + c, rw);
         tmem_ld_wait();
         float e[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float v = exp2f(fmaf(__uint_as_float(raw[i]), p.scale_log2, -m_new));
+          const float v = exp2f(fmaf(__uint_as_float(rw[i]), p.scale_log2, -m_new));
           e[i] = (c + i < kvalid) ? v : 0.f;
           psum += e[i];
         }
@@ -246,6 +294,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
           *reinterpret_cast<uint4*>(prow + ((c >> 3) + g) * (ATT_BM * 16)) = u;
         }
+      }
       }
       l_run = l_run * alpha + psum;
       m_run = m_new;
@@ -295,12 +344,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
 int attention_init() {
-  DFB_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  DFB_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   200 * 1024));
+  DFB_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    200 * 1024));
   return 0;
 }
@@ -344,8 +395,18 @@ int attention_launch(const __half* q, int ldq, const __half* k, int ldk, const _
   }
   AttParams p;
   p.out = out; p.ldo = ldo; p.heads = heads; p.Lq = Lq; p.Lk = Lk; p.d = d; p.dpad = dpad;
-  const int kb_max = dpad > 96 ? 64 : 128;  // keeps Q + 2x(K,V) + 2xP under the shared-memory limit
-  p.KB = std::min(kb_max, (Lk + 15) / 16 * 16);
+  // key-block size: 128 when the grid does not even fill the machine once (fewer, longer round trips
+  // per CTA) and the tiles fit; otherwise 64, which lets two CTAs share an SM
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
+  const long ctas = (long)((Lq + ATT_BM - 1) / ATT_BM) * B * heads;
+  const bool wide = (ctas <= n_sm) && dpad <= 96 && Lk > 64;
+  const int nq = wide ? 8 : 4;
+  p.KB = std::min(nq * 16, (Lk + 15) / 16 * 16);
+  {
+    const int need = 2 * nq * 16 + dpad;  // S double buffer + O
+    p.tmem_cols = need <= 256 ? 256 : 512;
+  }
   p.nblocks = (Lk + p.KB - 1) / p.KB;
   p.scale_log2 = scale * 1.4426950408889634f;
   static int swap = -1;
@@ -363,7 +424,10 @@ int attention_launch(const __half* q, int ldq, const __half* k, int ldk, const _
   dim3 grid((Lq + ATT_BM - 1) / ATT_BM, B * heads);
   note("attention", 4.0 * B * heads * (double)Lq * Lk * d,
        2.0 * B * heads * ((double)Lq * d * 2 + (double)Lk * d * 2), Lq, Lk, d, 1, grid.x * grid.y);
-  DFB_CUDA_OK(launch_pdl(attention_tcgen05_kernel, dim3(grid), dim3(ATT_THREADS), L.total + 128, stream, tq, tk, tv, p));
+  if (nq == 8)
+    DFB_CUDA_OK(launch_pdl(attention_tcgen05_kernel<8>, dim3(grid), dim3(ATT_THREADS), L.total + 128, stream, tq, tk, tv, p));
+  else
+    DFB_CUDA_OK(launch_pdl(attention_tcgen05_kernel<4>, dim3(grid), dim3(ATT_THREADS), L.total + 128, stream, tq, tk, tv, p));
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
 }
