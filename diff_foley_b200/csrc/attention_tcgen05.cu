@@ -45,7 +45,6 @@ struct AttParams {
   int ldo;
   int heads, Lq, Lk, d, dpad, KB, nblocks, tmem_cols;
   float scale_log2;  // d^-0.5 * log2(e)
-  int swap_lbo;      // debug: swap LBO/SBO of the un-swizzled descriptors
 };
 
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -159,7 +158,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     const uint32_t idesc_o = umma_idesc_f16(ATT_BM, p.dpad, 0, 1);  // B = V is MN-major
     const uint32_t q_lbo = ATT_BM * 16, k_lbo = KB * 16;
     auto desc = [&](uint32_t addr, uint32_t lbo, uint32_t sbo) {
-      return p.swap_lbo ? umma_desc_nosw(addr, sbo, lbo) : umma_desc_nosw(addr, lbo, sbo);
+      return umma_desc_nosw(addr, lbo, sbo);
     };
     const uint32_t sq = smem_u32(smem + L.off_q);
     auto issue_s = [&](int j) {
@@ -409,12 +408,6 @@ int attention_launch(const __half* q, int ldq, const __half* k, int ldk, const _
   }
   p.nblocks = (Lk + p.KB - 1) / p.KB;
   p.scale_log2 = scale * 1.4426950408889634f;
-  static int swap = -1;
-  if (swap < 0) {
-    const char* e = getenv("DFB_ATT_SWAP_LBO");
-    swap = (e && e[0] == '1') ? 1 : 0;
-  }
-  p.swap_lbo = swap;
   CUtensorMap tq, tk, tv;
   int rc = get_tmap(&tq, q, ldq, (long)B * Lq, dpad, ATT_BM);
   if (!rc) rc = get_tmap(&tk, k, ldk, (long)B * Lk, dpad, p.KB);

@@ -29,34 +29,12 @@ int kernels_init() {
   return rc;
 }
 
-// scratch for split-K when a GEMM is launched outside an engine (tests, single-op callers)
-static float* g_ws = nullptr;
-static size_t g_ws_bytes = 0;
-static int* g_counters = nullptr;
-static const int g_ncounters = 1 << 16;
-
-static int ensure_scratch(size_t bytes) {
-  if (g_counters == nullptr) {
-    DFB_CUDA_OK(cudaMalloc((void**)&g_counters, g_ncounters * sizeof(int)));
-    DFB_CUDA_OK(cudaMemset(g_counters, 0, g_ncounters * sizeof(int)));
-  }
-  if (bytes > g_ws_bytes) {
-    if (g_ws) cudaFree(g_ws);
-    g_ws = nullptr;
-    g_ws_bytes = 0;
-    DFB_CUDA_OK(cudaMalloc((void**)&g_ws, bytes));
-    DFB_CUDA_OK(cudaMemset(g_ws, 0, bytes));
-    g_ws_bytes = bytes;
-  }
-  return 0;
-}
-
 static int run_igemm(const __half* a, const __half* w, int N, const IGemmGeom& g, IGemmEpilogue ep,
                      int splits, cudaStream_t s) {
   int r = kernels_init();
   if (r) return r;
   IGemmPlan plan;
-  r = igemm_plan(&plan, a, w, N, g, ep, splits, nullptr, 0, nullptr, 0);
+  r = igemm_plan(&plan, a, w, N, g, ep, splits);
   if (r) return r;
   return igemm_launch(plan, s);
 }

@@ -99,9 +99,7 @@ struct IGemmPlan {
   IGemmEpilogue e;
   int M, N, K;       // logical sizes: M = B*T*H*W, K = ntaps*C
   int BN;            // tile N (64 or 128)
-  int tiles_m, tiles_n, splits;
-  float* ws;         // split-K workspace (tiles*splits*128*BN floats) or nullptr when splits==1
-  int* counters;     // per-tile arrival counters (zero-initialised, self-resetting)
+  int tiles_m, tiles_n, splits;  // splits == cluster size along grid.z
   // weights of the NEXT GEMM of the plan: every CTA issues an L2 prefetch for a slice of them, so the
   // next (weight-streaming) kernel finds its operand in L2 instead of waiting on cold HBM misses
   const void* next_w = nullptr;
@@ -109,11 +107,10 @@ struct IGemmPlan {
 };
 
 // Builds tensor maps + tiling for `A` (fp16 [B,T,H,W,C]) and `Wt` (fp16 [N, ntaps*C]).
-// splits==0 lets the planner pick a split-K factor that fills the 148 SMs.
+// splits==0 lets the planner pick tile width and split-K factor (= cluster size, <= 8) from its cost
+// model; split-K partials are reduced through distributed shared memory, no global workspace.
 int igemm_plan(IGemmPlan* plan, const __half* A, const __half* Wt, int N, const IGemmGeom& g,
-               const IGemmEpilogue& e, int splits, float* ws, size_t ws_bytes, int* counters,
-               int ncounters);
-size_t igemm_ws_bytes(const IGemmPlan& plan);
+               const IGemmEpilogue& e, int splits);
 int igemm_launch(const IGemmPlan& plan, cudaStream_t stream);
 // geometry for a "same"-padded stride-1 conv with a (kt,kh,kw) kernel over [B,T,H,W,C] (kt*kh*kw <= 9)
 IGemmGeom conv_taps_geom(int B, int T, int H, int W, int C, int kt, int kh, int kw);

@@ -166,12 +166,6 @@ struct dfb_unet {
   __half* kv16 = nullptr;
   int kv_b = 0, kv_len = 0;
 
-  // split-K workspace shared by all GEMMs (stream-ordered reuse)
-  float* ws = nullptr;
-  size_t ws_bytes = 0;
-  int* counters = nullptr;
-  int ncounters = 0;
-
   std::map<int, std::unique_ptr<Plan>> plans;
   long long last_launches = 0;
 
@@ -515,8 +509,7 @@ struct Builder {
   Plan* plan;
   int B;
   bool dry;  // first pass: only measure scratch requirements
-  size_t need16 = 0, need32 = 0, need_ws = 0;
-  int need_cnt = 0;
+  size_t need16 = 0, need32 = 0;
   __half* a16[3] = {nullptr, nullptr, nullptr};
   float* t32[3] = {nullptr, nullptr, nullptr};
   int rc = 0;
@@ -544,14 +537,11 @@ struct Builder {
       // plan with dummy (aligned, non-null) pointers just to learn tiling / workspace needs
       static __half* dummy = reinterpret_cast<__half*>(0x1000);
       IGemmEpilogue e2 = ep;
-      int r = igemm_plan(&ip, dummy, dummy, lin.N, g, e2, 0, reinterpret_cast<float*>(0x1000),
-                         (size_t)1 << 40, reinterpret_cast<int*>(0x1000), 1 << 30);
+      int r = igemm_plan(&ip, dummy, dummy, lin.N, g, e2, 0);
       if (r) { rc = r; return; }
-      need_ws = std::max(need_ws, igemm_ws_bytes(ip));
-      need_cnt = std::max(need_cnt, ip.tiles_m * ip.tiles_n);
       return;
     }
-    int r = igemm_plan(&ip, A, lin.w, lin.N, g, ep, 0, e->ws, e->ws_bytes, e->counters, e->ncounters);
+    int r = igemm_plan(&ip, A, lin.w, lin.N, g, ep, 0);
     if (r) { rc = r; return; }
     auto sp = std::make_shared<IGemmPlan>(ip);
     // link the previous GEMM to this one's weights (L2 prefetch of the next layer, see igemm kernel)
@@ -879,23 +869,6 @@ static int build_plan(dfb_unet* e, int B, Plan** out) {
     if (b.dry) {
       s_need16 = b.need16;
       s_need32 = b.need32;
-      // grow the shared split-K workspace if this batch size needs more
-      if (b.need_ws > e->ws_bytes) {
-        float* nw = nullptr;
-        if (cudaMalloc((void**)&nw, b.need_ws) != cudaSuccess) { set_error("ws cudaMalloc failed"); return DFB_E_CUDA; }
-        cudaMemset(nw, 0, b.need_ws);  // the atomic split-K path keeps its accumulation tiles at zero between launches
-        e->owned.push_back(nw);
-        e->ws = nw;
-        e->ws_bytes = b.need_ws;
-      }
-      if (b.need_cnt > e->ncounters) {
-        int* nc = nullptr;
-        if (cudaMalloc((void**)&nc, (size_t)b.need_cnt * sizeof(int)) != cudaSuccess) { set_error("counter cudaMalloc failed"); return DFB_E_CUDA; }
-        cudaMemset(nc, 0, (size_t)b.need_cnt * sizeof(int));
-        e->owned.push_back(nc);
-        e->counters = nc;
-        e->ncounters = b.need_cnt;
-      }
     }
   }
   *out = plan.get();
@@ -922,7 +895,7 @@ static int compute_context(dfb_unet* e, const float* ctx, int b_eff, int ctx_len
   if (r) return r;
   IGemmPlan ip;
   IGemmEpilogue ep = Builder::ep_f16(e->kv16, e->kv_all.N);
-  r = igemm_plan(&ip, e->ctx16, e->kv_all.w, e->kv_all.N, gemm_geom(M, D), ep, 1, nullptr, 0, nullptr, 0);
+  r = igemm_plan(&ip, e->ctx16, e->kv_all.w, e->kv_all.N, gemm_geom(M, D), ep, 1);
   if (r) return r;
   r = igemm_launch(ip, s);
   if (r) return r;

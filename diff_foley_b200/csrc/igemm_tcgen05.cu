@@ -530,11 +530,9 @@ static int num_sms() {
   return g_num_sms;
 }
 
-size_t igemm_ws_bytes(const IGemmPlan&) { return 0; }  // split-K reduces through DSMEM
 
 int igemm_plan(IGemmPlan* plan, const __half* A, const __half* Wt, int N, const IGemmGeom& g,
-               const IGemmEpilogue& e, int splits, float* ws, size_t ws_bytes, int* counters,
-               int ncounters) {
+               const IGemmEpilogue& e, int splits) {
   if (g.C % BLOCK_K != 0) {
     set_error("igemm: channel count must be a multiple of 64, got " + std::to_string(g.C));
     return -1;
@@ -590,9 +588,6 @@ int igemm_plan(IGemmPlan* plan, const __half* A, const __half* Wt, int N, const 
   const int BN = plan->BN;
   plan->tiles_n = (N + BN - 1) / BN;
   plan->splits = splits;
-  plan->ws = nullptr;
-  plan->counters = nullptr;
-  (void)ws; (void)ws_bytes; (void)counters; (void)ncounters;  // split-K no longer needs global scratch
   if ((e.out_f16 && (e.ldo % 8)) || (e.out_f32 && (e.ldo % 4)) || (e.residual && (e.ld_res % 4)) || (e.residual_f16 && (e.ld_res % 8)) ||
       (N % 16) != 0) {
     set_error("igemm: N must be a multiple of 16 and output/residual row strides 16-byte aligned");
