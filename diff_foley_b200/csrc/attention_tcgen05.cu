@@ -45,6 +45,7 @@ struct AttParams {
   int ldo;
   int heads, Lq, Lk, d, dpad, KB, nblocks, tmem_cols;
   float scale_log2;  // d^-0.5 * log2(e)
+  unsigned long long* trace;  // optional timeline record (diagnostics)
 };
 
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -100,6 +101,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) trace_mark(p.trace, 0);
   const int bh = blockIdx.y;
   const int b = bh / p.heads, h = bh % p.heads;
   const int q0 = blockIdx.x * ATT_BM;
@@ -129,6 +131,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   __syncthreads();
   tc_fence_after();
   pdl_wait();  // q/k/v come from the preceding GEMM
+  if (threadIdx.x == 0) trace_mark(p.trace, 1);
   pdl_launch_dependents();  // only after our own wait: at most two grids of the chain overlap
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_s[2] = {tmem_base, tmem_base + NQ * 16};  // S double buffer: 2 x (NQ*16 fp32 columns)
@@ -345,6 +348,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
+  if (threadIdx.x == 0) trace_mark(p.trace, 7);
 }
 
 int attention_init() {
@@ -408,6 +412,7 @@ int attention_launch(const __half* q, int ldq, const __half* k, int ldk, const _
   }
   p.nblocks = (Lk + p.KB - 1) / p.KB;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.trace = trace_record();
   CUtensorMap tq, tk, tv;
   int rc = get_tmap(&tq, q, ldq, (long)B * Lq, dpad, ATT_BM);
   if (!rc) rc = get_tmap(&tk, k, ldk, (long)B * Lk, dpad, p.KB);

@@ -39,6 +39,18 @@ inline void note(const char* kind, double flops, double bytes, int M = 0, int N 
   g_note.M = M; g_note.N = N; g_note.K = K; g_note.splits = splits; g_note.ctas = ctas;
 }
 
+// In-kernel timeline (dfb_unet_trace): while buf != nullptr the instrumented launchers hand their
+// kernel the 32-word record of op `next`; the engine sets `next` before each op of the plan.
+struct TraceState {
+  unsigned long long* buf = nullptr;
+  int cap = 0, next = 0;
+};
+extern TraceState g_trace;
+inline unsigned long long* trace_record() {
+  if (g_trace.buf == nullptr || g_trace.next >= g_trace.cap) return nullptr;
+  return g_trace.buf + 32ull * g_trace.next;
+}
+
 // Launch with the programmatic-dependent-launch attribute (DFB_NO_PDL=1 disables it).
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>

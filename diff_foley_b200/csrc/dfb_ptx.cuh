@@ -210,6 +210,48 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
   return v;
 }
 
+// asynchronous 16-byte store into the shared memory of a CTA of this cluster; the bytes are counted on
+// an mbarrier of the destination CTA (complete_tx), so the receiver needs no cluster-wide fence
+__device__ __forceinline__ void st_async_f4(uint32_t remote_addr, float a, float b, float c, float d,
+                                            uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                   remote_addr),
+               "f"(a), "f"(b), "f"(c), "f"(d), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// explicit shared-window accesses (the dynamic-smem base is re-aligned through integer arithmetic, after
+// which the compiler falls back to generic LD/ST for plain pointer dereferences)
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int2 lds_i2(uint32_t addr) {
+  int2 v;
+  asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void sts_i2(uint32_t addr, int a, int b) {
+  asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
 // ------------------------------------------------------------ programmatic dependent launch
 // Every kernel of the plan is launched with programmaticStreamSerialization: it may start while its
 // predecessor drains.  launch_dependents lets the successor's CTAs be scheduled early; wait blocks
@@ -223,6 +265,18 @@ __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ------------------------------------------------------------ in-kernel timeline (diagnostics)
+// dfb_unet_trace: every CTA folds its %globaltimer reading at mark k into (min, max) slots of the
+// launch's 32-word record (buffer pre-set to 0xFF: slot 2k = min t, slot 2k+1 = min ~t = ~max t).
+__device__ __forceinline__ void trace_mark(unsigned long long* tr, int k) {
+  if (tr != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMin(tr + 2 * k, t);
+    atomicMin(tr + 2 * k + 1, ~t);
+  }
+}
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 // exact-erf GELU (reference: F.gelu, attention_openai.py:44) with erf from Abramowitz-Stegun 7.1.26

@@ -28,6 +28,7 @@
 namespace dfb {
 
 thread_local LaunchNote g_note = {"none", 0, 0, 0, 0, 0, 1, 0};
+TraceState g_trace;
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 const char* last_error() { return g_err.c_str(); }
@@ -1225,6 +1226,59 @@ int dfb_unet_profile(dfb_handle h, const float* x, int x_repeat, const void* t, 
   cudaStreamDestroy(cs);
   for (int i = 0; i < n; ++i) infos[i].ms = (float)(acc[i] / iters);
   for (auto& e : ev) cudaEventDestroy(e);
+  return 0;
+}
+
+// In-kernel timeline of one graph-replayed forward: marks[i*32 + 2k] / [.. + 2k + 1] = first / last
+// %globaltimer (ns) any CTA of op i passed mark k (see trace_mark; 0 = kernel entry, 1 = after the
+// programmatic-dependent-launch wait, 2..6 = igemm phases, 7 = exit, 8..15 = finer igemm epilogue marks); all-ones where a mark was not hit.
+int dfb_unet_trace(dfb_handle h, const float* x, int x_repeat, const void* t, int t_is_float, float* out,
+                   int b_eff, unsigned long long* marks, int cap, int* n_ops, void* stream) {
+  if (!h || !x || !t || !out || !marks || !n_ops) { set_error("null argument"); return DFB_E_INVALID; }
+  if (!h->finalized) { set_error("trace before finalize"); return DFB_E_STATE; }
+  if (h->kv_b != b_eff) { set_error("trace: call dfb_unet_set_context for this batch size first"); return DFB_E_STATE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  Plan* p = nullptr;
+  int r = build_plan(h, b_eff, &p);
+  if (r) return r;
+  const int n = (int)p->ops.size();
+  *n_ops = n;
+  if (cap < n) { set_error("trace: marks array too small, need 32 words x " + std::to_string(n)); return DFB_E_INVALID; }
+  h->cur_x = x; h->cur_x_repeat = x_repeat; h->cur_t = t; h->cur_t_is_float = t_is_float; h->cur_out = out;
+  unsigned long long* dbuf = nullptr;
+  const size_t bytes = (size_t)n * 32 * sizeof(unsigned long long);
+  DFB_CUDA_OK(cudaMalloc(&dbuf, bytes));
+  cudaStream_t cs = nullptr;
+  DFB_CUDA_OK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  DFB_CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+  g_trace.buf = dbuf; g_trace.cap = n;
+  r = 0;
+  for (int i = 0; i < n && !r; ++i) {
+    g_trace.next = i;
+    r = p->ops[i](cs);
+  }
+  g_trace.buf = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+  if (r || ce != cudaSuccess) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaStreamDestroy(cs);
+    cudaFree(dbuf);
+    if (!r) set_error(std::string("trace: graph capture failed: ") + cudaGetErrorString(ce));
+    return r ? r : DFB_E_CUDA;
+  }
+  DFB_CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+  cudaGraphDestroy(graph);
+  for (int it = 0; it < 3; ++it) {  // the last replay is the one reported (caches / clocks warm)
+    DFB_CUDA_OK(cudaMemsetAsync(dbuf, 0xFF, bytes, s));
+    DFB_CUDA_OK(cudaGraphLaunch(exec, s));
+    DFB_CUDA_OK(cudaStreamSynchronize(s));
+  }
+  DFB_CUDA_OK(cudaMemcpy(marks, dbuf, bytes, cudaMemcpyDeviceToHost));
+  cudaGraphExecDestroy(exec);
+  cudaStreamDestroy(cs);
+  cudaFree(dbuf);
   return 0;
 }
 

@@ -35,7 +35,7 @@ namespace dfb {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 fp16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int IGEMM_THREADS = 192;
+constexpr int IGEMM_THREADS = 320;  // 1 TMA + 1 MMA + 4 TMEM-reader warps; all 10 run the epilogue's phase 2
 
 struct IGemmKParams {
   int M, N;
@@ -58,6 +58,7 @@ struct IGemmKParams {
   int splits;  // == cluster size along z (<= 8): the CTAs of one output tile reduce through DSMEM
   const uint8_t* next_w;  // optional: weights of the next GEMM, prefetched into L2 slice-wise
   unsigned long long next_w_bytes;
+  unsigned long long* trace;  // optional timeline record (diagnostics, see trace_mark)
 };
 
 template <int BN, int STAGES>
@@ -66,102 +67,27 @@ struct IGemmSmem {
   static constexpr int W_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  // full[STAGES], empty[STAGES], tmem_full, then tmem slot + flag
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16;
+  // full[STAGES], empty[STAGES], tmem_full, red (split-K partials landed), then tmem slot + flag, then
+  // the row table (m, sample)
+  static constexpr int ROW_OFFSET = BAR_OFFSET + (2 * STAGES + 2) * 8 + 16;
+  static constexpr int TOTAL = ROW_OFFSET + BLOCK_M * 8;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack to align the base to 1024 B
 };
 
-// Epilogue on 16 consecutive columns of one accumulator row.  Kept deliberately compact (rolled
-// column-chunk loops, one code path): the kernel is launched ~200x per UNet forward between other
-// kernels, so it starts with a cold instruction cache every time -- a 100 KB fully unrolled
-// epilogue cost ~10 us per launch in instruction fetch alone.
-__device__ __forceinline__ void epilogue16(const IGemmKParams& p, float (&v)[16], long m, int bs,
-                                           int n_base) {
-  if (p.bias != nullptr) {
-    const float4* bp = reinterpret_cast<const float4*>(p.bias + n_base);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 t = __ldg(bp + j);
-      v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
-    }
-  }
-  if (p.rowvec != nullptr) {
-    const float4* rp = reinterpret_cast<const float4*>(p.rowvec + (long)bs * p.ld_rowvec + n_base);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 t = __ldg(rp + j);
-      v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
-    }
-  }
-  if (p.residual != nullptr) {
-    const float4* rs = reinterpret_cast<const float4*>(p.residual + m * p.ld_res + n_base);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 t = rs[j];
-      v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
-    }
-  }
-  if (p.residual_f16 != nullptr) {
-    const uint4* rs = reinterpret_cast<const uint4*>(p.residual_f16 + m * p.ld_res + n_base);
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const uint4 u = rs[j];
-      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-      const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&u.z));
-      const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&u.w));
-      v[8 * j] += a.x; v[8 * j + 1] += a.y; v[8 * j + 2] += b.x; v[8 * j + 3] += b.y;
-      v[8 * j + 4] += c.x; v[8 * j + 5] += c.y; v[8 * j + 6] += d.x; v[8 * j + 7] += d.y;
-    }
-  }
-  if (p.act == ACT_SILU) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
-  } else if (p.act == ACT_RELU) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-  }
-  if (p.out_f32 != nullptr) {
-    float4* o = reinterpret_cast<float4*>(p.out_f32 + m * p.ldo + n_base);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  }
-  if (p.out_f16 != nullptr) {
-    uint4* o = reinterpret_cast<uint4*>(p.out_f16 + m * p.ldo + n_base);
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      __half2 h0 = __floats2half2_rn(v[8 * j], v[8 * j + 1]);
-      __half2 h1 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
-      __half2 h2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
-      __half2 h3 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
-      uint4 u;
-      u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-      u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-      o[j] = u;
-    }
-  }
+// ---- fused epilogue on one float4 (4 consecutive output columns of one row).  The accumulator tile
+// is first staged in shared memory (see the kernel), so here a warp covers whole rows: every global
+// access (bias / timestep-embedding vector / residual loads, fp32 / fp16 stores) is a contiguous
+// 256-512 B run per row instead of 32 rows x 16 B.
+__device__ __forceinline__ float4 f4_add(float4 a, const float4 b) {
+  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  return a;
 }
-
-// GEGLU on 16 value columns + their 16 gate columns -> 16 fp16 outputs (attention_openai.py:42-44)
-__device__ __forceinline__ void epilogue16_geglu(const IGemmKParams& p, const float (&a)[16],
-                                                 const float (&g)[16], long m, int nbv, int nbg,
-                                                 int out_col) {
-  float o[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j)
-    o[j] = (a[j] + __ldg(p.bias + nbv + j)) * gelu_erf_f(g[j] + __ldg(p.bias + nbg + j));
-  uint4* dst = reinterpret_cast<uint4*>(p.out_f16 + m * p.ldo + out_col);
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    __half2 h0 = __floats2half2_rn(o[8 * j], o[8 * j + 1]);
-    __half2 h1 = __floats2half2_rn(o[8 * j + 2], o[8 * j + 3]);
-    __half2 h2 = __floats2half2_rn(o[8 * j + 4], o[8 * j + 5]);
-    __half2 h3 = __floats2half2_rn(o[8 * j + 6], o[8 * j + 7]);
-    uint4 u;
-    u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-    u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-    dst[j] = u;
-  }
+__device__ __forceinline__ uint2 f4_to_h4(const float4 v) {
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&h0);
+  u.y = *reinterpret_cast<const uint32_t*>(&h1);
+  return u;
 }
 
 // STAGES-deep operand ring; the shallow-ring instantiations (<=3-4 stages, ~97 KB) let two CTAs share
@@ -178,10 +104,12 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* red_bar = tmem_full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(red_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) trace_mark(p.trace, 0);
 
   // ---- tile coordinates
   const int n0 = blockIdx.x * BN;
@@ -210,6 +138,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(red_bar, 1);
     fence_mbar_init();
     for (int i = 0; i < npre; ++i) {
       mbar_expect_tx(&full_bar[i], L::STAGE_BYTES);
@@ -224,24 +153,24 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   __syncthreads();
   tc_fence_after();
   pdl_wait();  // everything above overlapped the predecessor's tail; operands are valid from here
+  if (threadIdx.x == 0) trace_mark(p.trace, 1);
   pdl_launch_dependents();  // only after our own wait: at most two grids of the chain overlap
   const uint32_t tmem_base = *tmem_slot;
   const bool geglu = (p.act == ACT_GEGLU);
   const bool split = (p.splits > 1);
-  // output row owned by this thread when it acts as an epilogue thread (warps 2..5)
-  bool row_ok = false;
-  long m = 0;
-  int bs = 0;
-  if (warp >= 2) {
+  // row table: accumulator row r of this tile -> output row m (-1 = outside the tensor) and the
+  // sample it belongs to (for the per-sample vector); filled by the epilogue warps while the ring fills
+  const uint32_t row_tab = smem_u32(smem + L::ROW_OFFSET);
+  if (warp >= 2 && warp < 6) {
     const int r = (warp & 3) * 32 + lane;
     const int w_i = r % p.bw;
     const int h_i = (r / p.bw) % p.bh;
     const int t_i = (r / (p.bw * p.bh)) % p.bt;
     const int b_i = r / (p.bw * p.bh * p.bt);
     const int x = x0 + w_i, y = y0 + h_i, t = t0 + t_i, b = b0 + b_i;
-    row_ok = (x < p.W) && (y < p.H) && (t < p.T) && (b < p.B);
-    m = (((long)b * p.T + t) * p.H + y) * p.W + x;
-    bs = (p.rows_per_sample > 0) ? (int)(m / p.rows_per_sample) : b;
+    const bool row_ok = (x < p.W) && (y < p.H) && (t < p.T) && (b < p.B);
+    const int m = ((b * p.T + t) * p.H + y) * p.W + x;
+    sts_i2(row_tab + 8 * r, row_ok ? m : -1, (p.rows_per_sample > 0) ? m / p.rows_per_sample : b);
   }
 
   if (warp == 0) {
@@ -270,6 +199,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
       if (lane == 0) {
+        if (i == 0) trace_mark(p.trace, 2);
         const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
         const uint32_t sw = sa + L::A_BYTES;
         const uint64_t da = umma_desc_k_sw128(sa);
@@ -281,15 +211,15 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                       (i > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
-        if (i == nkb - 1) umma_commit(tmem_full_bar);
+        if (i == nkb - 1) {
+          umma_commit(tmem_full_bar);
+          trace_mark(p.trace, 3);
+        }
       }
       __syncwarp();
     }
   } else {
-    // ========================================================================= epilogue
-    const int sub = warp & 3;          // TMEM sub-partition this warp may read
-    const int r = sub * 32 + lane;     // accumulator row (= TMEM lane) owned by this thread
-    const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
+    // ================================================= epilogue, phase 0: wait for the accumulator
     if (warp == 2 && lane == 0 && p.next_w != nullptr) {
       // (an epilogue warp: idle until the accumulator is complete, and not on the TMA/MMA critical path)
       // software pipelining across layers: pull this CTA's slice of the next GEMM's weights into L2
@@ -306,101 +236,208 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     __syncwarp();
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    if (!split) {
-      // NB: tcgen05.ld is warp-collective (.sync.aligned): every lane loads, stores are predicated
-      if (!geglu) {
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 16) {
-          if (n0 + c >= p.N) break;
-          uint32_t raw[16];
-          tmem_ld_32x16(taddr + c, raw);
-          tmem_ld_wait();
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
-          if (row_ok) epilogue16(p, v, m, bs, n0 + c);
-        }
-      } else {
-        // tile columns [0,BN/2) are the value half, [BN/2,BN) the gate half of the same BN/2
-        // output features (weights were interleaved per tile when packed)
-#pragma unroll 1
-        for (int c = 0; c < BN / 2; c += 16) {
-          uint32_t ra[16], rg[16];
-          tmem_ld_32x16(taddr + c, ra);
-          tmem_ld_32x16(taddr + BN / 2 + c, rg);
-          tmem_ld_wait();
-          float a[16], g[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { a[j] = __uint_as_float(ra[j]); g[j] = __uint_as_float(rg[j]); }
-          if (row_ok) epilogue16_geglu(p, a, g, m, n0 + c, n0 + BN / 2 + c, blockIdx.x * (BN / 2) + c);
-        }
-      }
-    } else {
-      // split-K: park this CTA's partial tile in its own shared memory (the operand stages are dead
-      // once tmem_full fired) as [4-column group][row] float4, conflict-free for row-per-thread access
-      float4* stg = reinterpret_cast<float4*>(smem);
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
-        uint32_t raw[16];
-        tmem_ld_32x16(taddr + c, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          stg[((c >> 2) + j) * BLOCK_M + r] =
-              make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
-                          __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
-      }
-    }
+    if (warp == 2 && lane == 0) trace_mark(p.trace, 4);
   }
 
-  if (split) {
-    // ---- split-K reduction through distributed shared memory.  The `splits` CTAs of one output
-    // tile form a thread-block cluster (cluster dims (1,1,splits)); after a cluster barrier each CTA
-    // reduces every splits-th 16-column chunk by reading all peers' parked tiles with
-    // ld.shared::cluster in rank order -- deterministic, no atomics, no HBM/L2 workspace -- and runs
-    // the fused epilogue on it.
-    cluster_sync_all();
-    if (warp >= 2) {
-      const int sub = warp & 3;
-      const int r = sub * 32 + lane;
-      const uint32_t stg_base = smem_u32(smem);
-      const int S = p.splits, rank = blockIdx.z;
-      auto load16 = [&](int c, float (&v)[16]) {
+  // ---- epilogue, phase 1: TMEM -> shared-memory staging.  The `splits` CTAs of one output tile form a
+  // thread-block cluster (1,1,splits).  Accumulator row r is *pushed* (st.async: fire and forget, bytes
+  // counted on the receiver's mbarrier) into the staging area of the CTA that finishes it -- owner =
+  // r / R, R = ceil(128/splits) rows each -- slot = this CTA's K-split rank, so every CTA ends up with
+  // all the partials of its rows in its own shared memory and sums them in rank order: deterministic, no
+  // atomics, no global workspace, no remote round trips, no cluster-scope fence.  The staging area
+  // reuses the operand ring, so a peer may only write into it once this CTA's MMAs have drained: that
+  // is the one cluster barrier.  Layout: float4 [slot][row][group ^ (row & 7)] -- the XOR keeps both the
+  // row-per-thread writes here and the row-per-warp reads of phase 2 bank-conflict free.
+  const int S = p.splits, R = (BLOCK_M + S - 1) / S;
+  constexpr int G = BN / 4;  // float4 groups per accumulator row
+  const uint32_t stg = smem_u32(smem);
+  __syncwarp();  // re-converge the single-lane roles before the .aligned barriers
+  if (split) cluster_sync_all();
+  if (warp >= 2 && warp < 6) {
+    const int sub = warp & 3;          // TMEM sub-partition this warp may read
+    const int r = sub * 32 + lane;     // accumulator row (= TMEM lane) owned by this thread
+    const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
+    const int owner = r / R, lr = r - owner * R, sw = lr & 7;
+    const uint32_t loc = stg + (uint32_t)((((int)blockIdx.z * R + lr) * G) << 4);
+    const uint32_t dst = split ? mapa_shared(loc, (uint32_t)owner) : loc;
+    const uint32_t dbar = split ? mapa_shared(smem_u32(red_bar), (uint32_t)owner) : 0u;
+    // rows outside the tensor (M = 32 tiles: three quarters of them) are neither pushed nor summed
+    const bool push = lds_i2(row_tab + 8u * (uint32_t)r).x >= 0;
+    if (split && warp == 2) {
+      // this CTA finishes rows [rank*R, rank*R + Rz) and receives one partial of each valid one from
+      // every CTA of the cluster (itself included): arm the byte count (any time before the wait)
+      const int Rz = min(R, BLOCK_M - (int)blockIdx.z * R);
+      int nvalid = 0;
+      for (int i = lane; i < Rz; i += 32) nvalid += (lds_i2(row_tab + 8u * (uint32_t)((int)blockIdx.z * R + i)).x >= 0);
+      nvalid = __reduce_add_sync(0xffffffffu, nvalid);
+      if (lane == 0) mbar_expect_tx(red_bar, (uint32_t)(S * nvalid * min(BN, p.N - n0) * 4));
+    }
+    if (warp == 2 && lane == 0) trace_mark(p.trace, 12);
+    // NB: tcgen05.ld is warp-collective (.sync.aligned): every lane loads
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      if (n0 + c >= p.N) break;
+      if (c == 32 && warp == 2 && lane == 0) trace_mark(p.trace, 13);
+      uint32_t raw[32];
+      tmem_ld_32x32(taddr + c, raw);
+      tmem_ld_wait();
+      const int nj = (n0 + c + 16 >= p.N) ? 4 : 8;  // N is a multiple of 16: the tile may end mid-way
+      if (split) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        for (int j = 0; j < 8; ++j)
+          if (j < nj && push)
+            st_async_f4(dst + (uint32_t)((((c >> 2) + j) ^ sw) << 4), __uint_as_float(raw[4 * j]),
+                        __uint_as_float(raw[4 * j + 1]), __uint_as_float(raw[4 * j + 2]),
+                        __uint_as_float(raw[4 * j + 3]), dbar);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts_f4(dst + (uint32_t)((((c >> 2) + j) ^ sw) << 4), __uint_as_float(raw[4 * j]),
+                 __uint_as_float(raw[4 * j + 1]), __uint_as_float(raw[4 * j + 2]),
+                 __uint_as_float(raw[4 * j + 3]));
+      }
+    }
+    if (warp == 2 && lane == 0) trace_mark(p.trace, 5);
+  }
+  tc_fence_before();
+  if (split) mbar_wait_cluster(red_bar, 0); else __syncthreads();
+
+  // ---- epilogue, phase 2 (all warps): a warp takes whole rows -- lane = float4 group (two rows per pass
+  // when BN = 64) -- sums the K-split partials from local shared memory and runs the fused epilogue
+  // with coalesced global accesses.  The warps here run alone on their scheduler, so this code is bound
+  // by its own instruction latencies: UNR rows are processed as independent straight-line chains.
+  {
+    constexpr int NW = IGEMM_THREADS / 32;
+    const int rank = blockIdx.z;
+    const int Rz = min(R, BLOCK_M - rank * R);  // rows this CTA finishes (<= 0: none)
+    constexpr int RPW = 32 / G;                 // rows per warp pass (1 or 2)
+    constexpr int UNR = 4;
+    const int g = lane % G, sr = lane / G;
+    if (warp == 2 && lane == 0) trace_mark(p.trace, 8);
+    int nbatch = 0;
+    const uint32_t slot_stride = (uint32_t)(R * G) << 4;
+    const uint32_t tab = row_tab + 8u * (uint32_t)(rank * R);
+    if (!geglu) {
+      const bool lane_on = (n0 + 4 * g < p.N);
+      const int col = n0 + 4 * g;
+      float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane_on && p.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      const bool has_rv = (p.rowvec != nullptr), has_res = (p.residual != nullptr),
+                 has_res16 = (p.residual_f16 != nullptr);
+      const int colc = lane_on ? col : n0;  // clamped: the loads below are unconditional
+#pragma unroll 1
+      for (int base = warp * RPW + sr; base < Rz; base += NW * RPW * UNR) {
+        // every load of the batch is issued (at clamped, always-valid addresses) before any of them is
+        // consumed: no branch between a load and the next row's loads
+        int m[UNR], bsm[UNR];
+        uint32_t sa[UNR];
+        float4 acc[UNR], res[UNR], rv[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int lr = base + u * NW * RPW;
+          const int lrc = min(lr, Rz - 1);
+          const int2 ri = lds_i2(tab + 8u * (uint32_t)lrc);
+          m[u] = (lane_on && lr < Rz) ? ri.x : -1;
+          bsm[u] = ri.y;
+          sa[u] = stg + ((uint32_t)(lrc * G + (g ^ (lrc & 7))) << 4);
+          acc[u] = bias;
+          res[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          rv[u] = res[u];
+        }
+        if (has_rv) {
+#pragma unroll
+          for (int u = 0; u < UNR; ++u)
+            rv[u] = __ldg(reinterpret_cast<const float4*>(p.rowvec + (long)bsm[u] * p.ld_rowvec + colc));
+        }
+        if (has_res) {
+#pragma unroll
+          for (int u = 0; u < UNR; ++u)
+            res[u] = *reinterpret_cast<const float4*>(p.residual + (long)max(m[u], 0) * p.ld_res + colc);
+        } else if (has_res16) {
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            const uint2 h = *reinterpret_cast<const uint2*>(p.residual_f16 + (long)max(m[u], 0) * p.ld_res + colc);
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+            res[u] = make_float4(lo.x, lo.y, hi.x, hi.y);
+          }
+        }
 #pragma unroll 1
         for (int sidx = 0; sidx < S; ++sidx) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t local = stg_base + (uint32_t)((((c >> 2) + j) * BLOCK_M + r) * 16);
-            const float4 f = ld_dsmem_f4(mapa_shared(local, (uint32_t)sidx));
-            v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
+          for (int u = 0; u < UNR; ++u) acc[u] = f4_add(acc[u], lds_f4(sa[u] + (uint32_t)sidx * slot_stride));
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) acc[u] = f4_add(f4_add(acc[u], rv[u]), res[u]);
+        if (p.act == ACT_SILU) {
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            acc[u].x = silu_f(acc[u].x); acc[u].y = silu_f(acc[u].y);
+            acc[u].z = silu_f(acc[u].z); acc[u].w = silu_f(acc[u].w);
+          }
+        } else if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            acc[u].x = fmaxf(acc[u].x, 0.f); acc[u].y = fmaxf(acc[u].y, 0.f);
+            acc[u].z = fmaxf(acc[u].z, 0.f); acc[u].w = fmaxf(acc[u].w, 0.f);
           }
         }
-      };
-      if (row_ok) {
-        if (!geglu) {
+        if (p.out_f32 != nullptr) {
+#pragma unroll
+          for (int u = 0; u < UNR; ++u)
+            if (m[u] >= 0) *reinterpret_cast<float4*>(p.out_f32 + (long)m[u] * p.ldo + col) = acc[u];
+        }
+        if (p.out_f16 != nullptr) {
+#pragma unroll
+          for (int u = 0; u < UNR; ++u)
+            if (m[u] >= 0) *reinterpret_cast<uint2*>(p.out_f16 + (long)m[u] * p.ldo + col) = f4_to_h4(acc[u]);
+        }
+        if (warp == 2 && lane == 0 && nbatch < 3) trace_mark(p.trace, 9 + nbatch);
+        ++nbatch;
+      }
+    } else {
+      // GEGLU (attention_openai.py:42-44): tile columns [0,BN/2) are the value half, [BN/2,BN) the gate
+      // half of the same BN/2 output features (weights were interleaved per tile when packed).  A lane
+      // owns one float4 of values and the matching float4 of gates: G/2 lanes per row.
+      constexpr int G2 = G / 2, RPW2 = 32 / G2, UG = 4;
+      const int g2 = lane % G2, sr2 = lane / G2;
+      const int col = (int)blockIdx.x * (BN / 2) + 4 * g2;
+      const float4 bias_a = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4 * g2));
+      const float4 bias_g = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + BN / 2 + 4 * g2));
 #pragma unroll 1
-          for (int q = rank; q < BN / 16; q += S) {
-            const int c = q * 16;
-            if (n0 + c >= p.N) break;
-            float v[16];
-            load16(c, v);
-            epilogue16(p, v, m, bs, n0 + c);
-          }
-        } else {
+      for (int base = warp * RPW2 + sr2; base < Rz; base += NW * RPW2 * UG) {
+        int m[UG];
+        uint32_t sa[UG], sg[UG];
+        float4 va[UG], vg[UG];
+#pragma unroll
+        for (int u = 0; u < UG; ++u) {
+          const int lr = base + u * NW * RPW2;
+          const int lrc = min(lr, Rz - 1);
+          const int mi = lds_i2(tab + 8u * (uint32_t)lrc).x;
+          m[u] = (lr < Rz) ? mi : -1;
+          sa[u] = stg + ((uint32_t)(lrc * G + (g2 ^ (lrc & 7))) << 4);
+          sg[u] = stg + ((uint32_t)(lrc * G + ((g2 + G2) ^ (lrc & 7))) << 4);
+          va[u] = bias_a;
+          vg[u] = bias_g;
+        }
 #pragma unroll 1
-          for (int q = rank; q < BN / 32; q += S) {
-            const int c = q * 16;
-            float a[16], g[16];
-            load16(c, a);
-            load16(BN / 2 + c, g);
-            epilogue16_geglu(p, a, g, m, n0 + c, n0 + BN / 2 + c, blockIdx.x * (BN / 2) + c);
+        for (int sidx = 0; sidx < S; ++sidx) {
+#pragma unroll
+          for (int u = 0; u < UG; ++u) {
+            va[u] = f4_add(va[u], lds_f4(sa[u] + (uint32_t)sidx * slot_stride));
+            vg[u] = f4_add(vg[u], lds_f4(sg[u] + (uint32_t)sidx * slot_stride));
           }
+        }
+#pragma unroll
+        for (int u = 0; u < UG; ++u) {
+          float4 v = va[u];
+          v.x *= gelu_erf_f(vg[u].x); v.y *= gelu_erf_f(vg[u].y);
+          v.z *= gelu_erf_f(vg[u].z); v.w *= gelu_erf_f(vg[u].w);
+          if (m[u] >= 0) *reinterpret_cast<uint2*>(p.out_f16 + (long)m[u] * p.ldo + col) = f4_to_h4(v);
         }
       }
     }
-    cluster_sync_all();  // nobody's shared memory may go away while a peer is still reading it
+    if (warp == 2 && lane == 0) trace_mark(p.trace, 6);
   }
 
   // ---- teardown
@@ -410,6 +447,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);
   }
+  if (threadIdx.x == 0) trace_mark(p.trace, 7);
 }
 
 // =========================================================================== host side
@@ -681,6 +719,7 @@ int igemm_launch(const IGemmPlan& plan, cudaStream_t stream) {
   kp.splits = plan.splits;
   kp.next_w = reinterpret_cast<const uint8_t*>(plan.next_w);
   kp.next_w_bytes = plan.next_w_bytes;
+  kp.trace = trace_record();
   {
     const double out_b = (plan.e.out_f32 ? 4.0 : 0.0) + (plan.e.out_f16 ? 2.0 : 0.0);
     note(g.ntaps == 9 ? "igemm_conv3x3" : "igemm_linear", 2.0 * plan.M * plan.N * plan.K,

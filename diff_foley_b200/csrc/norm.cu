@@ -8,6 +8,8 @@
 // 682-684), Normalize (attention_openai.py:76-77, eps 1e-6), nn.LayerNorm
 // (attention_openai.py:203-205) and the th.cat of the skip connection (openai_unetmodel.py:736):
 // the kernel normalises across the *concatenation* of two sources without materialising it in fp32.
+#include <algorithm>
+
 #include "dfb_internal.h"
 #include "dfb_ptx.cuh"
 
@@ -41,10 +43,13 @@ constexpr int GN_MAXP = 8;   // float2 pairs held per thread
 __global__ void __launch_bounds__(GN_THREADS)
 groupnorm_kernel(const float* __restrict__ src0, int C0, const float* __restrict__ src1, int C1,
                  int HW, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 float eps, int silu, __half* __restrict__ out, __half* __restrict__ raw_out) {
+                 float eps, int silu, __half* __restrict__ out, __half* __restrict__ raw_out,
+                 unsigned long long* trace) {
   __shared__ float red[GN_THREADS / 32];
   __shared__ float part[2];  // this CTA's partial sum / partial centred sum of squares
+  if (threadIdx.x == 0) trace_mark(trace, 0);
   pdl_wait();
+  if (threadIdx.x == 0) trace_mark(trace, 1);
   pdl_launch_dependents();
   const int P = gridDim.x, rank = blockIdx.x;
   const int C = C0 + C1;
@@ -116,6 +121,7 @@ groupnorm_kernel(const float* __restrict__ src0, int C0, const float* __restrict
     }
   }
   if (P > 1) cluster_sync_all();  // peers may still be reading part[] of this CTA
+  if (threadIdx.x == 0) trace_mark(trace, 7);
 }
 
 
@@ -153,21 +159,27 @@ int groupnorm_launch(const float* src0, int C0, const float* src1, int C1, int B
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   DFB_CUDA_OK(cudaLaunchKernelEx(&cfg, groupnorm_kernel, src0, C0, src1, C1, HW, gamma, beta, eps, silu, out,
-                                 raw_out));
+                                 raw_out, trace_record()));
   return 0;
 }
 
 // One warp per row of fp32 [rows, C].  The row lives in registers (<= 10 float4 per lane, C <= 1280):
 // one global read, two-pass statistics on the registers, fp16 write.  4 warps per CTA so that even the
-// 128-row deep levels spread over 32 SMs.
+// 128-row deep levels spread over 32 SMs; up to 16 for the 2048-row level so that the grid stays at
+// ~128 CTAs (the in-kernel timeline showed the dependent launch being released ~2 us later behind a
+// 512-CTA grid than behind a 128-CTA one).
 constexpr int LN_WARPS = 4;
+constexpr int LN_MAX_WARPS = 16;
 constexpr int LN_MAXV = 10;
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__global__ void __launch_bounds__(LN_MAX_WARPS * 32)
 layernorm_kernel(const float* __restrict__ src, int rows, int C, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, float eps, __half* __restrict__ out) {
+                 const float* __restrict__ beta, float eps, __half* __restrict__ out,
+                 unsigned long long* trace) {
+  if (threadIdx.x == 0) trace_mark(trace, 0);
   pdl_wait();
+  if (threadIdx.x == 0) trace_mark(trace, 1);
   pdl_launch_dependents();
-  const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float4* x = reinterpret_cast<const float4*>(src + (size_t)row * C);
@@ -210,6 +222,7 @@ layernorm_kernel(const float* __restrict__ src, int rows, int C, const float* __
       *reinterpret_cast<uint2*>(o + 4 * i) = u;
     }
   }
+  if (lane == 0) trace_mark(trace, 7);
 }
 
 int layernorm_launch(const float* src, int rows, int C, const float* gamma, const float* beta,
@@ -218,9 +231,11 @@ int layernorm_launch(const float* src, int rows, int C, const float* gamma, cons
     set_error("layernorm: C must be a multiple of 4 and <= 1280");
     return -1;
   }
-  const int nblk = (rows + LN_WARPS - 1) / LN_WARPS;
+  const int warps = std::min(LN_MAX_WARPS, std::max(LN_WARPS, rows / 128));
+  const int nblk = (rows + warps - 1) / warps;
   note("layernorm", 0.0, (double)rows * C * 6.0, rows, C, 0, 1, nblk);
-  DFB_CUDA_OK(launch_pdl(layernorm_kernel, dim3(nblk), dim3(LN_WARPS * 32), 0, stream, src, rows, C, gamma, beta, eps, out));
+  DFB_CUDA_OK(launch_pdl(layernorm_kernel, dim3(nblk), dim3(warps * 32), 0, stream, src, rows, C, gamma, beta, eps, out,
+                         trace_record()));
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -299,6 +299,31 @@ class UNetModelB200(nn.Module):
                      splits=infos[i].splits, ctas=infos[i].ctas, flops=infos[i].flops,
                      bytes=infos[i].bytes, ms=infos[i].ms) for i in range(n_ops.value)]
 
+    def trace(self, x, timesteps, context):
+        """In-kernel %globaltimer timeline of one graph-replayed forward (diagnostics): int64 array
+        [n_ops, 16 marks, 2 (first, last)] in ns, -1 where a mark was not hit (see include/dfb.h)."""
+        import numpy as np
+        h = self.engine(x.device)
+        n = x.shape[0]
+        xin = x.detach().float().contiguous()
+        ctx = context.detach().float().contiguous()
+        t = timesteps.to(torch.int64).contiguous()
+        out = torch.empty(n, self.out_channels, *self.latent_size, device=x.device)
+        lib = L.lib()
+        cap = 4096
+        marks = (C.c_ulonglong * (32 * cap))()
+        n_ops = C.c_int(0)
+        with torch.cuda.device(x.device):
+            L.check(lib.dfb_unet_set_context(h, L.ptr(ctx), n, ctx.shape[1], L.cur_stream()), "set_context")
+            L.check(lib.dfb_unet_trace(h, L.ptr(xin), 1, L.ptr(t), 0, L.ptr(out), n, marks, cap,
+                                       C.byref(n_ops), L.cur_stream()), "dfb_unet_trace")
+        a = np.frombuffer(marks, dtype=np.uint64, count=32 * n_ops.value).reshape(n_ops.value, 16, 2).copy()
+        hit = a[:, :, 0] != np.uint64(0xFFFFFFFFFFFFFFFF)
+        a[:, :, 1] = ~a[:, :, 1]
+        res = a.astype(np.int64)
+        res[~hit] = -1
+        return res
+
     def debug_taps(self, b_eff):
         """Block outputs of the last forward at this batch size as {name: NCHW tensor} (test aid)."""
         lib, out = L.lib(), {}

@@ -98,6 +98,15 @@ typedef struct dfb_op_info {
 int dfb_unet_profile(dfb_handle h, const float* x_dev, int x_repeat, const void* t_dev, int t_is_float,
                      float* out_dev, int b_eff, int iters, dfb_op_info* infos, int cap, int* n_ops,
                      void* stream);
+/* In-kernel timeline of one graph-replayed UNet forward (diagnostics): for launch i and mark k,
+ * marks[32*i + 2*k] is the first and ~marks[32*i + 2*k + 1] the last %globaltimer reading (ns) at
+ * which a CTA of that launch passed the mark; mark 0 = kernel entry, 1 = programmatic-dependent-
+ * launch wait released, 2..6 = GEMM phases (first operand stage landed, last MMA issued, accumulator
+ * complete, epilogue done, split-K reduction done), 7 = exit, 8..15 = finer epilogue marks.  All-ones where a mark was not hit.
+ * `marks` is a HOST array of 32*cap words.  Context must have been set. */
+int dfb_unet_trace(dfb_handle h, const float* x_dev, int x_repeat, const void* t_dev, int t_is_float,
+                   float* out_dev, int b_eff, unsigned long long* marks, int cap, int* n_ops,
+                   void* stream);
 /* Debug/test aid: block outputs ("input_blocks.3", "middle_block", ...) of the plan for b_eff,
  * channels-last fp32 [b_eff, H, W, C].  With the environment variable DFB_DEBUG_TAPS=1 set before the
  * first forward every block output keeps its own buffer; otherwise only the skip-stack tensors
