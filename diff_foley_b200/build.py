@@ -23,7 +23,7 @@ def _stale():
         return True
     t = os.path.getmtime(LIB)
     for f in os.listdir(CSRC):
-        if f.endswith((".cu", ".cuh", ".h")) and os.path.getmtime(os.path.join(CSRC, f)) > t:
+        if f.endswith((".cu", ".cuh", ".h", ".inc")) and os.path.getmtime(os.path.join(CSRC, f)) > t:
             return True
     inc = os.path.join(HERE, "..", "include", "dfb.h")
     return os.path.getmtime(inc) > t

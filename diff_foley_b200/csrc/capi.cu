@@ -100,6 +100,8 @@ int dfb_conv_taps(const void* a, const void* w, int B, int T, int H, int W, int 
                    splits, (cudaStream_t)stream);
 }
 
+void dfb_debug_igemm_force(int bn, int deep) { igemm_force(bn, deep); }
+
 int dfb_im2col_f16(const void* src, void* dst, int NI, int H, int W, int C, int kh, int kw, int stride,
                    int pad, int Kpad, void* stream) {
   return im2col_f16_launch((const __half*)src, (__half*)dst, NI, H, W, C, kh, kw, stride, pad, Kpad,

@@ -112,6 +112,7 @@ struct IGemmPlan {
   int M, N, K;       // logical sizes: M = B*T*H*W, K = ntaps*C
   int BN;            // tile N (64 or 128)
   int tiles_m, tiles_n, splits;  // splits == cluster size along grid.z
+  int deep = -1;     // operand ring: 1 = deep (1 CTA/SM), 0 = shallow (2 CTAs/SM), -1 = launcher's default
   // weights of the NEXT GEMM of the plan: every CTA issues an L2 prefetch for a slice of them, so the
   // next (weight-streaming) kernel finds its operand in L2 instead of waiting on cold HBM misses
   const void* next_w = nullptr;
@@ -124,6 +125,9 @@ struct IGemmPlan {
 int igemm_plan(IGemmPlan* plan, const __half* A, const __half* Wt, int N, const IGemmGeom& g,
                const IGemmEpilogue& e, int splits);
 int igemm_launch(const IGemmPlan& plan, cudaStream_t stream);
+// tuning aid (tools/autotune_igemm.py): force the tile width (64 / 128, 0 = planner's choice) and the
+// ring depth (1 / 0, -1 = default) of every plan built afterwards
+void igemm_force(int bn, int deep);
 // geometry for a "same"-padded stride-1 conv with a (kt,kh,kw) kernel over [B,T,H,W,C] (kt*kh*kw <= 9)
 IGemmGeom conv_taps_geom(int B, int T, int H, int W, int C, int kt, int kh, int kw);
 // convenience geometry for a plain [M,K] x [N,K]^T GEMM

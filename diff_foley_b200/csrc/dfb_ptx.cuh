@@ -219,6 +219,15 @@ __device__ __forceinline__ void st_async_f4(uint32_t remote_addr, float a, float
                "f"(a), "f"(b), "f"(c), "f"(d), "r"(remote_bar)
                : "memory");
 }
+// bulk copy from this CTA's shared memory into the shared memory of a CTA of the cluster (TMA engine);
+// the bytes are counted on an mbarrier of the destination CTA: one complete_tx per copy
+__device__ __forceinline__ void bulk_copy_s2c(uint32_t remote_dst, uint32_t local_src, uint32_t bytes,
+                                              uint32_t remote_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   remote_dst),
+               "r"(local_src), "r"(bytes), "r"(remote_bar)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   do {

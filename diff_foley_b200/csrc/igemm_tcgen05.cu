@@ -70,7 +70,7 @@ struct IGemmSmem {
   // full[STAGES], empty[STAGES], tmem_full, red (split-K partials landed), then tmem slot + flag, then
   // the row table (m, sample)
   static constexpr int ROW_OFFSET = BAR_OFFSET + (2 * STAGES + 2) * 8 + 16;
-  static constexpr int TOTAL = ROW_OFFSET + BLOCK_M * 8;
+  static constexpr int TOTAL = ROW_OFFSET + BLOCK_M * 8 + 16;  // + 128 valid-row bits
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack to align the base to 1024 B
 };
 
@@ -239,38 +239,33 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     if (warp == 2 && lane == 0) trace_mark(p.trace, 4);
   }
 
-  // ---- epilogue, phase 1: TMEM -> shared-memory staging.  The `splits` CTAs of one output tile form a
-  // thread-block cluster (1,1,splits).  Accumulator row r is *pushed* (st.async: fire and forget, bytes
-  // counted on the receiver's mbarrier) into the staging area of the CTA that finishes it -- owner =
-  // r / R, R = ceil(128/splits) rows each -- slot = this CTA's K-split rank, so every CTA ends up with
-  // all the partials of its rows in its own shared memory and sums them in rank order: deterministic, no
-  // atomics, no global workspace, no remote round trips, no cluster-scope fence.  The staging area
-  // reuses the operand ring, so a peer may only write into it once this CTA's MMAs have drained: that
-  // is the one cluster barrier.  Layout: float4 [slot][row][group ^ (row & 7)] -- the XOR keeps both the
-  // row-per-thread writes here and the row-per-warp reads of phase 2 bank-conflict free.
+  // ---- epilogue, phase 1: TMEM -> shared-memory staging (the operand ring is dead once the accumulator
+  // is complete).  Layout: rows of BN floats, float4 group g of row r at [r][g ^ (lr & 7)] -- the XOR
+  // keeps both the row-per-thread writes here and the row-per-warp reads of phase 2 bank-conflict free.
+  // Split-K: the `splits` CTAs of one output tile form a thread-block cluster (1,1,splits); CTA z
+  // finishes rows [z*R, (z+1)*R) of the tile, R = ceil(128/splits), lr = r - z*R.  After ONE cluster
+  // barrier (every CTA's ring is dead and its tile staged) each CTA sends every peer that peer's rows of
+  // its partial tile as one contiguous bulk copy (cp.async.bulk shared::cta -> shared::cluster, bytes
+  // counted on the receiver's mbarrier), into slot [sender rank] of the receive area behind the local
+  // tile.  The receiver then sums the slots in rank order from its own shared memory: deterministic, no
+  // atomics, no global workspace, no per-element remote traffic (DSMEM moves ~20 B/clk/SM at best, and a
+  // per-float4 st.async costs one mbarrier update each -- both measured).
   const int S = p.splits, R = (BLOCK_M + S - 1) / S;
   constexpr int G = BN / 4;  // float4 groups per accumulator row
-  const uint32_t stg = smem_u32(smem);
-  __syncwarp();  // re-converge the single-lane roles before the .aligned barriers
-  if (split) cluster_sync_all();
+  constexpr uint32_t ROWB = BN * 4;
+  const uint32_t tile = smem_u32(smem);             // this CTA's (partial) accumulator tile, 128 rows
+  const uint32_t rcv = tile + BLOCK_M * ROWB;        // split-K: [slot][R rows] received partials
+  uint32_t* vmask = reinterpret_cast<uint32_t*>(smem + L::ROW_OFFSET + BLOCK_M * 8);  // valid-row bits
   if (warp >= 2 && warp < 6) {
     const int sub = warp & 3;          // TMEM sub-partition this warp may read
     const int r = sub * 32 + lane;     // accumulator row (= TMEM lane) owned by this thread
     const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
-    const int owner = r / R, lr = r - owner * R, sw = lr & 7;
-    const uint32_t loc = stg + (uint32_t)((((int)blockIdx.z * R + lr) * G) << 4);
-    const uint32_t dst = split ? mapa_shared(loc, (uint32_t)owner) : loc;
-    const uint32_t dbar = split ? mapa_shared(smem_u32(red_bar), (uint32_t)owner) : 0u;
-    // rows outside the tensor (M = 32 tiles: three quarters of them) are neither pushed nor summed
-    const bool push = lds_i2(row_tab + 8u * (uint32_t)r).x >= 0;
-    if (split && warp == 2) {
-      // this CTA finishes rows [rank*R, rank*R + Rz) and receives one partial of each valid one from
-      // every CTA of the cluster (itself included): arm the byte count (any time before the wait)
-      const int Rz = min(R, BLOCK_M - (int)blockIdx.z * R);
-      int nvalid = 0;
-      for (int i = lane; i < Rz; i += 32) nvalid += (lds_i2(row_tab + 8u * (uint32_t)((int)blockIdx.z * R + i)).x >= 0);
-      nvalid = __reduce_add_sync(0xffffffffu, nvalid);
-      if (lane == 0) mbar_expect_tx(red_bar, (uint32_t)(S * nvalid * min(BN, p.N - n0) * 4));
+    const int lr = r % R, sw = lr & 7;
+    const uint32_t dst = tile + (uint32_t)r * ROWB;
+    if (split) {
+      // rows outside the tensor (M = 32 tiles: three quarters of them) are neither sent nor summed
+      const uint32_t vm = __ballot_sync(0xffffffffu, lds_i2(row_tab + 8u * (uint32_t)r).x >= 0);
+      if (lane == 0) vmask[sub] = vm;
     }
     if (warp == 2 && lane == 0) trace_mark(p.trace, 12);
     // NB: tcgen05.ld is warp-collective (.sync.aligned): every lane loads
@@ -281,26 +276,37 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       uint32_t raw[32];
       tmem_ld_32x32(taddr + c, raw);
       tmem_ld_wait();
-      const int nj = (n0 + c + 16 >= p.N) ? 4 : 8;  // N is a multiple of 16: the tile may end mid-way
-      if (split) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j < nj && push)
-            st_async_f4(dst + (uint32_t)((((c >> 2) + j) ^ sw) << 4), __uint_as_float(raw[4 * j]),
-                        __uint_as_float(raw[4 * j + 1]), __uint_as_float(raw[4 * j + 2]),
-                        __uint_as_float(raw[4 * j + 3]), dbar);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          sts_f4(dst + (uint32_t)((((c >> 2) + j) ^ sw) << 4), __uint_as_float(raw[4 * j]),
-                 __uint_as_float(raw[4 * j + 1]), __uint_as_float(raw[4 * j + 2]),
-                 __uint_as_float(raw[4 * j + 3]));
-      }
+      for (int j = 0; j < 8; ++j)
+        sts_f4(dst + (uint32_t)((((c >> 2) + j) ^ sw) << 4), __uint_as_float(raw[4 * j]),
+               __uint_as_float(raw[4 * j + 1]), __uint_as_float(raw[4 * j + 2]),
+               __uint_as_float(raw[4 * j + 3]));
     }
+    if (split) fence_proxy_async_smem();  // the staged tile is read by the bulk-copy engine
     if (warp == 2 && lane == 0) trace_mark(p.trace, 5);
   }
   tc_fence_before();
-  if (split) mbar_wait_cluster(red_bar, 0); else __syncthreads();
+  __syncwarp();  // re-converge the single-lane roles before the .aligned barriers
+  if (!split) {
+    __syncthreads();
+  } else {
+    cluster_sync_all();
+    if (warp == 2 && lane < S) {
+      // lane z: the span of valid rows among those CTA z finishes -> one bulk copy to CTA z; the lane
+      // whose z is this CTA's own rank also arms the receive barrier with what all S senders deliver
+      const int z = lane;
+      int lo = BLOCK_M, hi = 0;
+      for (int r = z * R; r < min(BLOCK_M, (z + 1) * R); ++r)
+        if ((vmask[r >> 5] >> (r & 31)) & 1u) { lo = min(lo, r); hi = r + 1; }
+      const uint32_t bytes = hi > lo ? (uint32_t)(hi - lo) * ROWB : 0u;
+      if (z == (int)blockIdx.z) mbar_expect_tx(red_bar, (uint32_t)S * bytes);
+      if (bytes)
+        bulk_copy_s2c(mapa_shared(rcv + (uint32_t)((int)blockIdx.z * R + (lo - z * R)) * ROWB, (uint32_t)z),
+                      tile + (uint32_t)lo * ROWB, bytes, mapa_shared(smem_u32(red_bar), (uint32_t)z));
+    }
+    mbar_wait_cluster(red_bar, 0);
+  }
+  const uint32_t stg = split ? rcv : tile;
 
   // ---- epilogue, phase 2 (all warps): a warp takes whole rows -- lane = float4 group (two rows per pass
   // when BN = 64) -- sums the K-split partials from local shared memory and runs the fused epilogue
@@ -569,6 +575,16 @@ static int num_sms() {
 }
 
 
+// Measured plan table: (M, N, K, taps, GEGLU?) -> (tile width, K-splits, ring depth), generated on a
+// B200 by tools/autotune_igemm.py from event-timed, cold-weight replays of every distinct GEMM of the
+// UNet plans (B_eff = 2 and 16).  Shapes that are not listed fall back to the cost model below.
+struct IGemmTuned { int M, N, K, ntaps, geglu, bn, splits, deep; };
+static const IGemmTuned kTuned[] = {
+#include "igemm_tuned.inc"
+    {0, 0, 0, 0, 0, 0, 0, 0}};
+static int g_force_bn = 0, g_force_deep = -1;
+void igemm_force(int bn, int deep) { g_force_bn = bn; g_force_deep = deep; }
+
 int igemm_plan(IGemmPlan* plan, const __half* A, const __half* Wt, int N, const IGemmGeom& g,
                const IGemmEpilogue& e, int splits) {
   if (g.C % BLOCK_K != 0) {
@@ -594,6 +610,12 @@ int igemm_plan(IGemmPlan* plan, const __half* A, const __half* Wt, int N, const 
             tt = (g.T + g.bt - 1) / g.bt, tb = (g.B + g.bb - 1) / g.bb;
   plan->tiles_m = tw * th * tt * tb;
   const int kb_total = g.ntaps * (g.C / BLOCK_K);
+  plan->deep = g_force_deep;
+  static const bool no_table = getenv("DFB_NO_TUNED") != nullptr;
+  const IGemmTuned* tuned = nullptr;
+  if (splits == 0 && g_force_bn == 0 && !no_table)
+    for (const IGemmTuned* t = kTuned; t->M; ++t)
+      if (t->M == plan->M && t->N == N && t->K == plan->K && t->ntaps == g.ntaps && t->geglu == (int)geglu) { tuned = t; break; }
   // ---- tile width BN and split-K factor (= cluster size, <= 8).  Tiny cost model: a CTA moves one
   // (A rows that exist + BN weight rows) x 128 B stage per k-block at ~55 GB/s (its share of L2
   // bandwidth), pays ~1 us for a DSMEM reduction, and the grid runs in ceil(ctas / #SMs) waves.
@@ -602,7 +624,8 @@ int igemm_plan(IGemmPlan* plan, const __half* A, const __half* Wt, int N, const 
     const int rows_per_tile = std::min(BLOCK_M, plan->M);  // rows TMA really fetches (rest is zero fill)
     double best = 1e30;
     int best_bn = 128, best_s = 1;
-    const int bn_lo = (geglu ? 128 : 64), bn_hi = (N <= 64 ? 64 : 128);
+    int bn_lo = (geglu ? 128 : 64), bn_hi = (N <= 64 ? 64 : 128);
+    if (g_force_bn == 64 || g_force_bn == 128) bn_lo = bn_hi = (geglu ? 128 : g_force_bn);
     for (int bn = bn_hi; bn >= bn_lo; bn /= 2) {
       const int tiles = plan->tiles_m * ((N + bn - 1) / bn);
       const int smax = (splits > 0) ? splits : 8;
@@ -622,6 +645,11 @@ int igemm_plan(IGemmPlan* plan, const __half* A, const __half* Wt, int N, const 
     }
     plan->BN = best_bn;
     splits = best_s;
+    if (tuned != nullptr && tuned->splits <= kb_total) {
+      plan->BN = tuned->bn;
+      splits = tuned->splits;
+      if (plan->deep < 0) plan->deep = tuned->deep;
+    }
   }
   const int BN = plan->BN;
   plan->tiles_n = (N + BN - 1) / BN;
@@ -732,7 +760,9 @@ int igemm_launch(const IGemmPlan& plan, cudaStream_t stream) {
   // resident -- and stream their first weight tiles -- while this kernel is still running.  Measured
   // 3.37 ms/step vs 3.46 with the deep ring everywhere (DFB_SHALLOW=0 selects the deep ring).
   static const int force_shallow = getenv("DFB_SHALLOW") ? atoi(getenv("DFB_SHALLOW")) : -1;
-  const bool shallow = (force_shallow != 0);
+  // split-K with 128-wide tiles stages its own tile (64 KB) plus the received partials (<= 68 KB): that
+  // needs the deep ring's shared memory
+  const bool shallow = (plan.deep >= 0 ? plan.deep == 0 : force_shallow != 0) && !(plan.BN == 128 && plan.splits > 1);
   if (plan.BN == 64) return shallow ? launch_t<64, 4>(plan, kp, stream) : launch_t<64, 8>(plan, kp, stream);
   return shallow ? launch_t<128, 3>(plan, kp, stream) : launch_t<128, 6>(plan, kp, stream);
 }

@@ -98,6 +98,9 @@ typedef struct dfb_op_info {
 int dfb_unet_profile(dfb_handle h, const float* x_dev, int x_repeat, const void* t_dev, int t_is_float,
                      float* out_dev, int b_eff, int iters, dfb_op_info* infos, int cap, int* n_ops,
                      void* stream);
+/* Tuning aid (tools/autotune_igemm.py): force the GEMM tile width (64 / 128; 0 = planner's choice) and
+ * operand-ring depth (1 deep / 0 shallow; -1 = default) of every GEMM planned afterwards. */
+void dfb_debug_igemm_force(int bn, int deep);
 /* In-kernel timeline of one graph-replayed UNet forward (diagnostics): for launch i and mark k,
  * marks[32*i + 2*k] is the first and ~marks[32*i + 2*k + 1] the last %globaltimer reading (ns) at
  * which a CTA of that launch passed the mark; mark 0 = kernel entry, 1 = programmatic-dependent-
