@@ -35,7 +35,7 @@ namespace dfb {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 fp16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int IGEMM_THREADS = 320;  // 1 TMA + 1 MMA + 4 TMEM-reader warps; all 10 run the epilogue's phase 2
+constexpr int IGEMM_THREADS = 320;  // 1 TMA + 1 MMA warp; warps 2..5 read TMEM, warps 2..9 finish the tile
 
 struct IGemmKParams {
   int M, N;
@@ -149,15 +149,6 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     tmem_alloc(tmem_slot, BN);  // BN fp32 columns x 128 lanes (power of two >= 32)
     tmem_relinquish();
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  pdl_wait();  // everything above overlapped the predecessor's tail; operands are valid from here
-  if (threadIdx.x == 0) trace_mark(p.trace, 1);
-  pdl_launch_dependents();  // only after our own wait: at most two grids of the chain overlap
-  const uint32_t tmem_base = *tmem_slot;
-  const bool geglu = (p.act == ACT_GEGLU);
-  const bool split = (p.splits > 1);
   // row table: accumulator row r of this tile -> output row m (-1 = outside the tensor) and the
   // sample it belongs to (for the per-sample vector); filled by the epilogue warps while the ring fills
   const uint32_t row_tab = smem_u32(smem + L::ROW_OFFSET);
@@ -173,6 +164,80 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     sts_i2(row_tab + 8 * r, row_ok ? m : -1, (p.rows_per_sample > 0) ? m / p.rows_per_sample : b);
   }
 
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();  // everything above overlapped the predecessor's tail; operands are valid from here
+  if (threadIdx.x == 0) trace_mark(p.trace, 1);
+  pdl_launch_dependents();  // only after our own wait: at most two grids of the chain overlap
+  const uint32_t tmem_base = *tmem_slot;
+  const bool geglu = (p.act == ACT_GEGLU);
+  const bool split = (p.splits > 1);
+
+  // ---- epilogue geometry (phase 2 below).  Warps 2..9 finish the tile: a warp takes whole rows, lane =
+  // float4 group (two rows per pass when BN = 64).  Their operands do not depend on the accumulator, so
+  // the first batch (bias, per-sample vector, residual) is fetched NOW, under the main loop.
+  constexpr int G = BN / 4;            // float4 groups per accumulator row
+  constexpr int NW = IGEMM_THREADS / 32 - 2;
+  constexpr int RPW = 32 / G;          // rows per warp pass (1 or 2)
+  constexpr int UNR = 4;
+  constexpr int STEP = NW * RPW * UNR;
+  const int S = p.splits, R = (BLOCK_M + S - 1) / S;
+  const int Rz = min(R, BLOCK_M - (int)blockIdx.z * R);  // rows this CTA finishes (<= 0: none)
+  const uint32_t tab = row_tab + 8u * (uint32_t)((int)blockIdx.z * R);
+  const int g = lane % G, sr = lane / G;
+  const bool lane_on = (n0 + 4 * g < p.N);
+  const int col = n0 + 4 * g;
+  const int colc = lane_on ? col : n0;  // clamped: the operand loads are unconditional
+  const bool has_rv = (p.rowvec != nullptr), has_res = (p.residual != nullptr),
+             has_res16 = (p.residual_f16 != nullptr);
+  const int base0 = (warp - 2) * RPW + sr;
+  struct EpiOps {
+    int m[UNR];
+    float4 rv[UNR], res[UNR];
+  };
+  // every load of a batch is issued (at clamped, always-valid addresses) before any of them is consumed
+  auto epi_fetch = [&](int base, EpiOps& o) {
+    int bsm[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int lr = base + u * NW * RPW;
+      const int2 ri = lds_i2(tab + 8u * (uint32_t)max(min(lr, Rz - 1), 0));
+      o.m[u] = (lane_on && lr < Rz) ? ri.x : -1;
+      bsm[u] = ri.y;
+      o.rv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      o.res[u] = o.rv[u];
+    }
+    if (has_rv) {
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+        o.rv[u] = __ldg(reinterpret_cast<const float4*>(p.rowvec + (long)bsm[u] * p.ld_rowvec + colc));
+    }
+    if (has_res) {
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+        o.res[u] = *reinterpret_cast<const float4*>(p.residual + (long)max(o.m[u], 0) * p.ld_res + colc);
+    } else if (has_res16) {
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const uint2 h = *reinterpret_cast<const uint2*>(p.residual_f16 + (long)max(o.m[u], 0) * p.ld_res + colc);
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+        o.res[u] = make_float4(lo.x, lo.y, hi.x, hi.y);
+      }
+    }
+  };
+  EpiOps ops;
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), bias_g = bias;
+  if (warp >= 2) {
+    if (!geglu) {
+      if (lane_on && p.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      if (base0 < Rz) epi_fetch(base0, ops);
+    } else {
+      bias = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4 * (lane % (G / 2))));
+      bias_g = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + BN / 2 + 4 * (lane % (G / 2))));
+    }
+  }
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
@@ -250,8 +315,6 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   // tile.  The receiver then sums the slots in rank order from its own shared memory: deterministic, no
   // atomics, no global workspace, no per-element remote traffic (DSMEM moves ~20 B/clk/SM at best, and a
   // per-float4 st.async costs one mbarrier update each -- both measured).
-  const int S = p.splits, R = (BLOCK_M + S - 1) / S;
-  constexpr int G = BN / 4;  // float4 groups per accumulator row
   constexpr uint32_t ROWB = BN * 4;
   const uint32_t tile = smem_u32(smem);             // this CTA's (partial) accumulator tile, 128 rows
   const uint32_t rcv = tile + BLOCK_M * ROWB;        // split-K: [slot][R rows] received partials
@@ -308,65 +371,25 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   }
   const uint32_t stg = split ? rcv : tile;
 
-  // ---- epilogue, phase 2 (all warps): a warp takes whole rows -- lane = float4 group (two rows per pass
-  // when BN = 64) -- sums the K-split partials from local shared memory and runs the fused epilogue
-  // with coalesced global accesses.  The warps here run alone on their scheduler, so this code is bound
-  // by its own instruction latencies: UNR rows are processed as independent straight-line chains.
-  {
-    constexpr int NW = IGEMM_THREADS / 32;
-    const int rank = blockIdx.z;
-    const int Rz = min(R, BLOCK_M - rank * R);  // rows this CTA finishes (<= 0: none)
-    constexpr int RPW = 32 / G;                 // rows per warp pass (1 or 2)
-    constexpr int UNR = 4;
-    const int g = lane % G, sr = lane / G;
+  // ---- epilogue, phase 2 (warps 2..9): sum the K-split partials from local shared memory and run the
+  // fused epilogue with coalesced global accesses.  These warps run alone on their schedulers, so the
+  // code is bound by its own instruction latencies: UNR rows are processed as independent straight-line
+  // chains.
+  if (warp >= 2) {
     if (warp == 2 && lane == 0) trace_mark(p.trace, 8);
     int nbatch = 0;
     const uint32_t slot_stride = (uint32_t)(R * G) << 4;
-    const uint32_t tab = row_tab + 8u * (uint32_t)(rank * R);
     if (!geglu) {
-      const bool lane_on = (n0 + 4 * g < p.N);
-      const int col = n0 + 4 * g;
-      float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lane_on && p.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-      const bool has_rv = (p.rowvec != nullptr), has_res = (p.residual != nullptr),
-                 has_res16 = (p.residual_f16 != nullptr);
-      const int colc = lane_on ? col : n0;  // clamped: the loads below are unconditional
 #pragma unroll 1
-      for (int base = warp * RPW + sr; base < Rz; base += NW * RPW * UNR) {
-        // every load of the batch is issued (at clamped, always-valid addresses) before any of them is
-        // consumed: no branch between a load and the next row's loads
-        int m[UNR], bsm[UNR];
+      for (int base = base0; base < Rz; base += STEP) {
+        if (base != base0) epi_fetch(base, ops);  // (the first batch was fetched under the main loop)
+        float4 acc[UNR];
         uint32_t sa[UNR];
-        float4 acc[UNR], res[UNR], rv[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-          const int lr = base + u * NW * RPW;
-          const int lrc = min(lr, Rz - 1);
-          const int2 ri = lds_i2(tab + 8u * (uint32_t)lrc);
-          m[u] = (lane_on && lr < Rz) ? ri.x : -1;
-          bsm[u] = ri.y;
+          const int lrc = min(base + u * NW * RPW, Rz - 1);
           sa[u] = stg + ((uint32_t)(lrc * G + (g ^ (lrc & 7))) << 4);
           acc[u] = bias;
-          res[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          rv[u] = res[u];
-        }
-        if (has_rv) {
-#pragma unroll
-          for (int u = 0; u < UNR; ++u)
-            rv[u] = __ldg(reinterpret_cast<const float4*>(p.rowvec + (long)bsm[u] * p.ld_rowvec + colc));
-        }
-        if (has_res) {
-#pragma unroll
-          for (int u = 0; u < UNR; ++u)
-            res[u] = *reinterpret_cast<const float4*>(p.residual + (long)max(m[u], 0) * p.ld_res + colc);
-        } else if (has_res16) {
-#pragma unroll
-          for (int u = 0; u < UNR; ++u) {
-            const uint2 h = *reinterpret_cast<const uint2*>(p.residual_f16 + (long)max(m[u], 0) * p.ld_res + colc);
-            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
-            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
-            res[u] = make_float4(lo.x, lo.y, hi.x, hi.y);
-          }
         }
 #pragma unroll 1
         for (int sidx = 0; sidx < S; ++sidx) {
@@ -374,7 +397,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           for (int u = 0; u < UNR; ++u) acc[u] = f4_add(acc[u], lds_f4(sa[u] + (uint32_t)sidx * slot_stride));
         }
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) acc[u] = f4_add(f4_add(acc[u], rv[u]), res[u]);
+        for (int u = 0; u < UNR; ++u) acc[u] = f4_add(f4_add(acc[u], ops.rv[u]), ops.res[u]);
         if (p.act == ACT_SILU) {
 #pragma unroll
           for (int u = 0; u < UNR; ++u) {
@@ -391,12 +414,12 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         if (p.out_f32 != nullptr) {
 #pragma unroll
           for (int u = 0; u < UNR; ++u)
-            if (m[u] >= 0) *reinterpret_cast<float4*>(p.out_f32 + (long)m[u] * p.ldo + col) = acc[u];
+            if (ops.m[u] >= 0) *reinterpret_cast<float4*>(p.out_f32 + (long)ops.m[u] * p.ldo + col) = acc[u];
         }
         if (p.out_f16 != nullptr) {
 #pragma unroll
           for (int u = 0; u < UNR; ++u)
-            if (m[u] >= 0) *reinterpret_cast<uint2*>(p.out_f16 + (long)m[u] * p.ldo + col) = f4_to_h4(acc[u]);
+            if (ops.m[u] >= 0) *reinterpret_cast<uint2*>(p.out_f16 + (long)ops.m[u] * p.ldo + col) = f4_to_h4(acc[u]);
         }
         if (warp == 2 && lane == 0 && nbatch < 3) trace_mark(p.trace, 9 + nbatch);
         ++nbatch;
@@ -407,11 +430,9 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       // owns one float4 of values and the matching float4 of gates: G/2 lanes per row.
       constexpr int G2 = G / 2, RPW2 = 32 / G2, UG = 4;
       const int g2 = lane % G2, sr2 = lane / G2;
-      const int col = (int)blockIdx.x * (BN / 2) + 4 * g2;
-      const float4 bias_a = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4 * g2));
-      const float4 bias_g = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + BN / 2 + 4 * g2));
+      const int colg = (int)blockIdx.x * (BN / 2) + 4 * g2;
 #pragma unroll 1
-      for (int base = warp * RPW2 + sr2; base < Rz; base += NW * RPW2 * UG) {
+      for (int base = (warp - 2) * RPW2 + sr2; base < Rz; base += NW * RPW2 * UG) {
         int m[UG];
         uint32_t sa[UG], sg[UG];
         float4 va[UG], vg[UG];
@@ -423,7 +444,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           m[u] = (lr < Rz) ? mi : -1;
           sa[u] = stg + ((uint32_t)(lrc * G + (g2 ^ (lrc & 7))) << 4);
           sg[u] = stg + ((uint32_t)(lrc * G + ((g2 + G2) ^ (lrc & 7))) << 4);
-          va[u] = bias_a;
+          va[u] = bias;
           vg[u] = bias_g;
         }
 #pragma unroll 1
@@ -439,7 +460,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           float4 v = va[u];
           v.x *= gelu_erf_f(vg[u].x); v.y *= gelu_erf_f(vg[u].y);
           v.z *= gelu_erf_f(vg[u].z); v.w *= gelu_erf_f(vg[u].w);
-          if (m[u] >= 0) *reinterpret_cast<uint2*>(p.out_f16 + (long)m[u] * p.ldo + col) = f4_to_h4(v);
+          if (m[u] >= 0) *reinterpret_cast<uint2*>(p.out_f16 + (long)m[u] * p.ldo + colg) = f4_to_h4(v);
         }
       }
     }

@@ -2,7 +2,8 @@
 //
 // Both read the fp32 residual stream (channels-last) and emit the fp16 tile the following tensor-core
 // GEMM / conv pulls in through TMA, so the normalised activation is written exactly once, at half
-// width.  Statistics are two-pass (mean, then centred second moment) in fp32 like ATen's.
+// width.  Statistics are fp32: LayerNorm two-pass (mean, then centred second moment) on registers,
+// GroupNorm one pass about a pivot (no cancellation, one reduction round).
 //
 // Replaces: GroupNorm32 + SiLU (reference util.py:214-216, openai_unetmodel.py:201-203,225-228,
 // 682-684), Normalize (attention_openai.py:76-77, eps 1e-6), nn.LayerNorm
@@ -38,15 +39,15 @@ constexpr int GN_MAXP = 8;   // float2 pairs held per thread
 
 // grid = (P, 32 groups, B) with cluster dims (P,1,1): the P CTAs of a cluster share one (sample,
 // group) slab, split along the pixel axis.  Each thread keeps its <= 8 channel pairs in registers (one
-// global read, no shared-memory slab); the group statistics are two-pass (mean, then centred second
-// moment, like ATen) with the per-CTA partials exchanged through distributed shared memory.
+// global read, no shared-memory slab); the group statistics are one pass about a pivot (see below), the
+// per-CTA partials exchanged through distributed shared memory.
 __global__ void __launch_bounds__(GN_THREADS)
 groupnorm_kernel(const float* __restrict__ src0, int C0, const float* __restrict__ src1, int C1,
                  int HW, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float eps, int silu, __half* __restrict__ out, __half* __restrict__ raw_out,
                  unsigned long long* trace) {
-  __shared__ float red[GN_THREADS / 32];
-  __shared__ float part[2];  // this CTA's partial sum / partial centred sum of squares
+  __shared__ float red[GN_THREADS / 32], red2[GN_THREADS / 32];
+  __shared__ __align__(8) float part[2];  // this CTA's partial sums (s1, s2)
   if (threadIdx.x == 0) trace_mark(trace, 0);
   pdl_wait();
   if (threadIdx.x == 0) trace_mark(trace, 1);
@@ -62,8 +63,15 @@ groupnorm_kernel(const float* __restrict__ src0, int C0, const float* __restrict
   const int npx = max(0, min(px_per, HW - px0));
   const int npairs = npx * hp;
 
+  // One-pass statistics about a pivot (the slab's first element, the same for every CTA of the cluster):
+  // s1 = sum(x - piv), s2 = sum((x - piv)^2).  The pivot is a sample of the data, so |mean - piv| is of
+  // the order of the standard deviation and var = s2/n - (s1/n)^2 loses no precision to cancellation --
+  // and one block reduction + one cluster exchange replace the two of a mean-then-variance scheme
+  // (this kernel is a pure latency chain: load, reduce, exchange, write).
+  const float piv = (cbase < C0) ? __ldg(src0 + (size_t)b * HW * C0 + cbase)
+                                 : __ldg(src1 + (size_t)b * HW * C1 + (cbase - C0));
   float2 v[GN_MAXP];
-  float s = 0.f;
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int k = 0; k < GN_MAXP; ++k) {
     const int i = threadIdx.x + k * GN_THREADS;
@@ -73,35 +81,40 @@ groupnorm_kernel(const float* __restrict__ src0, int C0, const float* __restrict
       const int c = cbase + 2 * (i % hp);
       v[k] = (c < C0) ? *reinterpret_cast<const float2*>(src0 + ((size_t)b * HW + px) * C0 + c)
                       : *reinterpret_cast<const float2*>(src1 + ((size_t)b * HW + px) * C1 + (c - C0));
-      s += v[k].x + v[k].y;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < GN_MAXP; ++k) {
+    if (threadIdx.x + k * GN_THREADS < npairs) {
+      const float dx = v[k].x - piv, dy = v[k].y - piv;
+      s1 += dx + dy;
+      s2 += dx * dx + dy * dy;
     }
   }
   const float inv_n = 1.f / (float)(HW * cpg);
-  auto cluster_total = [&](float local, int slot) -> float {
-    const float t = block_sum<GN_THREADS>(local, red);
-    if (P == 1) return t;
-    if (threadIdx.x == 0) part[slot] = t;
-    cluster_sync_all();
-    float tot = 0.f;
-    const uint32_t a = smem_u32(&part[slot]);
-    for (int r = 0; r < P; ++r) {
-      float x;
-      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(x) : "r"(mapa_shared(a, (uint32_t)r)) : "memory");
-      tot += x;
-    }
-    return tot;
-  };
-  const float mean = cluster_total(s, 0) * inv_n;
-  float q = 0.f;
-#pragma unroll
-  for (int k = 0; k < GN_MAXP; ++k) {
-    const int i = threadIdx.x + k * GN_THREADS;
-    if (i < npairs) {
-      const float dx = v[k].x - mean, dy = v[k].y - mean;
-      q += dx * dx + dy * dy;
+  {
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[warp] = s1; red2[warp] = s2; }
+    __syncthreads();
+    s1 = warp_sum(lane < GN_THREADS / 32 ? red[lane] : 0.f);
+    s2 = warp_sum(lane < GN_THREADS / 32 ? red2[lane] : 0.f);
+    if (P > 1) {
+      if (threadIdx.x == 0) { part[0] = s1; part[1] = s2; }
+      cluster_sync_all();
+      const uint32_t a0 = smem_u32(&part[0]);
+      s1 = 0.f; s2 = 0.f;
+      for (int r = 0; r < P; ++r) {
+        float x, y;
+        asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(mapa_shared(a0, (uint32_t)r)) : "memory");
+        s1 += x; s2 += y;
+      }
     }
   }
-  const float var = cluster_total(q, 1) * inv_n;
+  const float dm = s1 * inv_n;
+  const float mean = piv + dm;
+  const float var = fmaxf(s2 * inv_n - dm * dm, 0.f);
   const float rstd = rsqrtf(var + eps);
 #pragma unroll
   for (int k = 0; k < GN_MAXP; ++k) {
