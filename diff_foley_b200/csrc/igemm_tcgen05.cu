@@ -309,7 +309,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   // keeps both the row-per-thread writes here and the row-per-warp reads of phase 2 bank-conflict free.
   // Split-K: the `splits` CTAs of one output tile form a thread-block cluster (1,1,splits); CTA z
   // finishes rows [z*R, (z+1)*R) of the tile, R = ceil(128/splits), lr = r - z*R.  After ONE cluster
-  // barrier (every CTA's ring is dead and its tile staged) each CTA sends every peer that peer's rows of
+  // barrier (every CTA's ring is dead; no memory ordering needed) each CTA sends every peer that peer's rows of
   // its partial tile as one contiguous bulk copy (cp.async.bulk shared::cta -> shared::cluster, bytes
   // counted on the receiver's mbarrier), into slot [sender rank] of the receive area behind the local
   // tile.  The receiver then sums the slots in rank order from its own shared memory: deterministic, no
@@ -319,6 +319,10 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   const uint32_t tile = smem_u32(smem);             // this CTA's (partial) accumulator tile, 128 rows
   const uint32_t rcv = tile + BLOCK_M * ROWB;        // split-K: [slot][R rows] received partials
   uint32_t* vmask = reinterpret_cast<uint32_t*>(smem + L::ROW_OFFSET + BLOCK_M * 8);  // valid-row bits
+  __syncwarp();  // re-converge the single-lane roles before the .aligned barriers
+  // "this CTA's operand ring is dead" (warps >= 2 get here after the accumulator completed): arrive now,
+  // wait only before the copies are issued -- the barrier's latency hides behind the staging below
+  if (split) cluster_arrive_relaxed();
   if (warp >= 2 && warp < 6) {
     const int sub = warp & 3;          // TMEM sub-partition this warp may read
     const int r = sub * 32 + lane;     // accumulator row (= TMEM lane) owned by this thread
@@ -349,11 +353,9 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     if (warp == 2 && lane == 0) trace_mark(p.trace, 5);
   }
   tc_fence_before();
-  __syncwarp();  // re-converge the single-lane roles before the .aligned barriers
-  if (!split) {
-    __syncthreads();
-  } else {
-    cluster_sync_all();
+  __syncthreads();  // the staged tile (and the valid-row bits) are complete
+  if (split) {
+    cluster_wait();
     if (warp == 2 && lane < S) {
       // lane z: the span of valid rows among those CTA z finishes -> one bulk copy to CTA z; the lane
       // whose z is this CTA's own rank also arms the receive barrier with what all S senders deliver
@@ -367,6 +369,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         bulk_copy_s2c(mapa_shared(rcv + (uint32_t)((int)blockIdx.z * R + (lo - z * R)) * ROWB, (uint32_t)z),
                       tile + (uint32_t)lo * ROWB, bytes, mapa_shared(smem_u32(red_bar), (uint32_t)z));
     }
+    if (warp == 2 && lane == 0) trace_mark(p.trace, 15);
     mbar_wait_cluster(red_bar, 0);
   }
   const uint32_t stg = split ? rcv : tile;
@@ -396,6 +399,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
           for (int u = 0; u < UNR; ++u) acc[u] = f4_add(acc[u], lds_f4(sa[u] + (uint32_t)sidx * slot_stride));
         }
+        if (warp == 2 && lane == 0 && nbatch == 0) trace_mark(p.trace, 14);
 #pragma unroll
         for (int u = 0; u < UNR; ++u) acc[u] = f4_add(f4_add(acc[u], ops.rv[u]), ops.res[u]);
         if (p.act == ACT_SILU) {

@@ -47,8 +47,20 @@ groupnorm_kernel(const float* __restrict__ src0, int C0, const float* __restrict
                  float eps, int silu, __half* __restrict__ out, __half* __restrict__ raw_out,
                  unsigned long long* trace) {
   __shared__ float red[GN_THREADS / 32], red2[GN_THREADS / 32];
-  __shared__ __align__(8) float part[2];  // this CTA's partial sums (s1, s2)
+  __shared__ __align__(8) float2 inbox[8];   // (s1, s2) of every CTA of the cluster, pushed by its owner
+  __shared__ __align__(8) uint64_t inbox_bar;
   if (threadIdx.x == 0) trace_mark(trace, 0);
+  if (gridDim.x > 1) {
+    // partial sums are exchanged by st.async pushes counted on the receiver's mbarrier: no cluster-scope
+    // fence (a release/acquire cluster barrier costs a MEMBAR.ALL.GPU, > 1 us here).  The relaxed
+    // arrive/wait pair only proves that every peer's barrier exists; its latency hides under the loads.
+    if (threadIdx.x == 0) {
+      mbar_init(&inbox_bar, 1);
+      fence_mbar_init();
+      mbar_expect_tx(&inbox_bar, gridDim.x * 8u);
+    }
+    cluster_arrive_relaxed();
+  }
   pdl_wait();
   if (threadIdx.x == 0) trace_mark(trace, 1);
   pdl_launch_dependents();
@@ -101,15 +113,13 @@ groupnorm_kernel(const float* __restrict__ src0, int C0, const float* __restrict
     s1 = warp_sum(lane < GN_THREADS / 32 ? red[lane] : 0.f);
     s2 = warp_sum(lane < GN_THREADS / 32 ? red2[lane] : 0.f);
     if (P > 1) {
-      if (threadIdx.x == 0) { part[0] = s1; part[1] = s2; }
-      cluster_sync_all();
-      const uint32_t a0 = smem_u32(&part[0]);
+      cluster_wait();
+      if (threadIdx.x < P)
+        st_async_f2(mapa_shared(smem_u32(&inbox[rank]), threadIdx.x), s1, s2,
+                    mapa_shared(smem_u32(&inbox_bar), threadIdx.x));
+      mbar_wait_cluster(&inbox_bar, 0);
       s1 = 0.f; s2 = 0.f;
-      for (int r = 0; r < P; ++r) {
-        float x, y;
-        asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(mapa_shared(a0, (uint32_t)r)) : "memory");
-        s1 += x; s2 += y;
-      }
+      for (int r = 0; r < P; ++r) { s1 += inbox[r].x; s2 += inbox[r].y; }  // rank order: deterministic
     }
   }
   const float dm = s1 * inv_n;
@@ -133,7 +143,6 @@ groupnorm_kernel(const float* __restrict__ src0, int C0, const float* __restrict
       if (raw_out != nullptr) *reinterpret_cast<__half2*>(raw_out + o) = __floats2half2_rn(v[k].x, v[k].y);
     }
   }
-  if (P > 1) cluster_sync_all();  // peers may still be reading part[] of this CTA
   if (threadIdx.x == 0) trace_mark(trace, 7);
 }
 

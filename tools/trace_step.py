@@ -50,7 +50,7 @@ for i in range(n):
     body = (x1 - w0) / 1e3
     print(f"{i:3d} {p['kind']:14s} {p['M']:5d} {p['N']:6d} {p['K']:6d} {p['splits']:2d} {p['ctas']:4d} | {(e0 - t0) / 1e3:8.1f} {(w0 - e0) / 1e3:6.1f} {body:6.1f} {gap:6.1f} |"
           f" {rel(2, 0):5.1f} {rel(3, 1):5.1f} {rel(4, 1):5.1f} {rel(5, 1):5.1f} {rel(6, 1):5.1f} {rel(7, 1):5.1f}"
-          + ("" if tr[i, 8, 0] < 0 else f" | p1 {rel(12, 0):5.1f} {rel(13, 0):5.1f} | p2 {rel(8, 0):5.1f} {rel(9, 0):5.1f} {rel(10, 0):5.1f} {rel(11, 0):5.1f}"))
+          + ("" if tr[i, 8, 0] < 0 else f" | p1 {rel(12, 0):5.1f} {rel(13, 0):5.1f} cp {rel(15, 0):5.1f} {rel(15, 1):5.1f} | p2 {rel(8, 0):5.1f} {rel(8, 1):5.1f} sum {rel(14, 0):5.1f} b {rel(9, 0):5.1f} {rel(10, 0):5.1f} {rel(11, 0):5.1f}"))
     a = agg.setdefault(p["kind"], [0, 0.0, 0.0])
     a[0] += 1; a[1] += body; a[2] += 0.0 if gap != gap else gap
     prev_exit = x1
