@@ -248,6 +248,13 @@ def run_ours(args):
         ach_gbs = ig_bytes / (ig_ms / 1e3) / 1e9
         ach_tf = ig_flops / (ig_ms / 1e3) / 1e12
         hbm_bound = (ig_bytes / pk["hbm"] / 1e9) >= (ig_flops / pk["tf_sust"] / 1e12)
+        # DRAM traffic of the same 195 launches from the committed ncu pass (B_eff = 2 only); null otherwise
+        traffic, traffic_src = None, None
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_igemm_dram_traffic.json")
+        if C == 1 and os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            traffic = tj["dram_bytes_read_per_forward"] + tj["dram_bytes_write_per_forward"]
+            traffic_src = tj["source"]
         roofline = {
             "kernel": "igemm_tcgen05_kernel (all Linear / 1x1 / 3x3 conv launches of one UNet forward)",
             "bound": "hbm" if hbm_bound else "tensor",
@@ -255,7 +262,7 @@ def run_ours(args):
             "peak": pk["hbm"] if hbm_bound else pk["tf_sust"],
             "unit": "GB/s" if hbm_bound else "TFLOP/s",
             "frac": (ach_gbs / pk["hbm"]) if hbm_bound else (ach_tf / pk["tf_sust"]),
-            "traffic": None, "peak_source": pk["src"],
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk["src"],
             "launches_per_forward": len(ig), "kernel_ms_per_forward": ig_ms,
             "kernel_ms_per_forward_event_profile": ig_ms_raw, "all_kernels_ms_per_forward_event_profile": all_ms,
             "how": "algorithmic bytes (or flops) of the 195 igemm launches of one UNet forward / (igemm share of the per-launch event profile x graph-timed UNet step)",

@@ -238,3 +238,55 @@ def test_ddim_step_bit_exact():
     r0 = (x - f(c1) * e) / f(c2)
     rp = f(c3) * r0 + f(c4) * e
     assert torch.equal(p0, r0) and torch.equal(xp, rp)
+
+
+# every (tile width, ring depth, K-splits) candidate the measured plan table (igemm_tuned.inc) may pick:
+# ragged M (rows outside the tensor are neither exchanged nor stored), N that ends mid-tile, split
+# factors that do not divide 128 rows, residual + bias epilogue; split-K results are bit-reproducible
+@pytest.mark.parametrize("M,N,K", [(32, 1280, 1280), (200, 320, 640), (512, 640, 1920)])
+@pytest.mark.parametrize("bn,deep", [(64, 0), (64, 1), (128, 1)])
+def test_gemm_forced_plans(M, N, K, bn, deep):
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(DEV).half()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV).half()
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV)
+    ref = a.float() @ w.float().t() + bias + res
+    lib = L.lib()
+    try:
+        lib.dfb_debug_igemm_force(bn, deep)
+        for splits in (1, 2, 3, 5, 7, 8):
+            out = gemm(a, w, bias=bias, residual=res, splits=splits)
+            assert rel_l2(out, ref) < 2e-6, (bn, deep, splits)
+            if splits > 1:
+                again = gemm(a, w, bias=bias, residual=res, splits=splits)
+                assert torch.equal(out, again), "split-K reduction must be deterministic"
+    finally:
+        lib.dfb_debug_igemm_force(0, -1)
+
+
+@pytest.mark.parametrize("splits", [3, 6])
+def test_conv3x3_split_ragged_batch(splits):
+    """3x3 conv at the 2x8 level with B = 3 (the 128-row tile holds 8 samples: 5 of them do not exist)."""
+    g = torch.Generator(device="cpu").manual_seed(17 + splits)
+    B, H, W, C, N = 3, 2, 8, 256, 320
+    a = torch.randn(B, H, W, C, generator=g).to(DEV).half()
+    w = (torch.randn(N, C, 3, 3, generator=g) / math.sqrt(9 * C)).to(DEV).half()
+    bias = torch.randn(N, generator=g).to(DEV)
+    rowvec = torch.randn(B, N, generator=g).to(DEV)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = F.conv2d(a.float().permute(0, 3, 1, 2), w.float(), bias, padding=1)
+        ref = (ref + rowvec[:, :, None, None]).permute(0, 2, 3, 1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    lib = L.lib()
+    try:
+        for bn, deep in ((64, 0), (128, 1)):
+            lib.dfb_debug_igemm_force(bn, deep)
+            out = conv3x3(a, w, bias, rowvec, None, splits)
+            assert torch.isfinite(out).all()
+            assert rel_l2(out, ref) < 3e-6, (bn, deep)
+    finally:
+        lib.dfb_debug_igemm_force(0, -1)

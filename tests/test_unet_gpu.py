@@ -165,3 +165,27 @@ def test_classifier_guided_sampling_matches_reference():
     err = rel_l2(samples, g["samples"])
     print(f"\n[parity] classifier-guided DDIM-25: latent rel-L2 = {err:.3e}")
     assert err < 2e-2
+
+
+def test_in_kernel_timeline():
+    """dfb_unet_trace: every instrumented launch reports entry <= wait-release <= exit, launches are
+    ordered in time, and tracing leaves the forward's result untouched."""
+    cfg = unet_oracle.small_unet_cfg()
+    sd = unet_oracle.seeded_state_dict(cfg, 123)
+    unet = UNetModelB200(**unet_kwargs(cfg))
+    unet.load_state_dict(sd)
+    unet = unet.to("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 4, cfg["latent_h"], cfg["latent_w"], generator=g).cuda()
+    ctx = torch.randn(2, cfg["context_len"], cfg["context_dim"], generator=g).cuda()
+    t = torch.full((2,), 500, dtype=torch.long, device="cuda")
+    before = unet(x, t, context=ctx).clone()
+    tr = unet.trace(x, t, ctx)
+    assert tr.ndim == 3 and tr.shape[1:] == (16, 2)
+    hit = tr[:, 0, 0] >= 0
+    assert hit.sum() > 0.8 * len(tr)            # the elementwise kernels are not instrumented
+    e, w, x_ = tr[hit, 0, 0], tr[hit, 1, 0], tr[hit, 7, 1]
+    assert (e <= w).all() and (w <= x_).all()
+    assert (w[1:] >= w[:-1]).all()              # dependent launches release in order
+    assert 0 < (x_.max() - e.min()) < 50_000_000  # one small forward: well under 50 ms
+    assert torch.equal(unet(x, t, context=ctx), before)
