@@ -63,6 +63,7 @@ SIGNATURES = {
     "dfb_unet_destroy": (_i, [_vp]),
     "dfb_gemm": (_i, [_vp, _vp, _i, _i, _i, _fp, _fp, _i, _fp, _vp, _i, _vp]),
     "dfb_conv3x3": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _i, _fp, _vp, _i, _vp]),
+    "dfb_conv3x3_cat": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _vp, _i, _vp]),
     "dfb_conv_taps": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _fp, _vp, _i, _fp, _vp, _i, _vp]),
     "dfb_im2col_f16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dfb_pool2d_f16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

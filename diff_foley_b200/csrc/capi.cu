@@ -80,6 +80,27 @@ int dfb_conv3x3(const void* a, const void* w, int B, int H, int W, int C, int N,
                    (cudaStream_t)stream);
 }
 
+int dfb_conv3x3_cat(const void* a, const void* a2, int C2, const void* w, int B, int H, int W, int C, int N,
+                    const float* bias, const float* bias2, const float* residual, float* out_f32,
+                    void* out_f16, int splits, void* stream) {
+  if (!a || !a2 || !w || B < 1 || H < 1 || W < 1 || C2 < 1) { set_error("dfb_conv3x3_cat: bad argument"); return DFB_E_INVALID; }
+  IGemmEpilogue ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.out_f32 = out_f32;
+  ep.out_f16 = (__half*)out_f16;
+  ep.ldo = N;
+  ep.bias = bias;
+  ep.rowvec = bias2;  // a second bias vector: "per-sample vector" with stride 0
+  ep.ld_rowvec = 0;
+  ep.rows_per_sample = H * W;
+  ep.residual = residual;
+  ep.ld_res = N;
+  IGemmGeom g = conv3x3_geom(B, H, W, C);
+  g.C2 = C2;
+  g.A2 = (const __half*)a2;
+  return run_igemm((const __half*)a, (const __half*)w, N, g, ep, splits, (cudaStream_t)stream);
+}
+
 int dfb_conv_taps(const void* a, const void* w, int B, int T, int H, int W, int C, int N, int kt, int kh,
                   int kw, const float* bias, const void* residual_f16, int act, float* out_f32,
                   void* out_f16, int splits, void* stream) {

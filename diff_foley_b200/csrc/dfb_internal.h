@@ -89,6 +89,11 @@ struct IGemmGeom {
   int bb, bt, bh, bw;
   int ntaps;            // 1, 3 (temporal) or 9 (3x3)
   int8_t dt[9], dh[9], dw[9];
+  // optional second A source: an fp16 channels-last tensor [B,T,H,W,C2] over the same positions whose C2
+  // channels are appended to K after the taps (tap offset 0) -- a 1x1 conv on another tensor summed into
+  // the same accumulator (the ResBlock skip connection fused into conv2); weights [N, ntaps*C + C2]
+  int C2;
+  const __half* A2;
 };
 
 struct IGemmEpilogue {
@@ -106,7 +111,7 @@ struct IGemmEpilogue {
 };
 
 struct IGemmPlan {
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmA, tmW, tmA2;
   IGemmGeom g;
   IGemmEpilogue e;
   int M, N, K;       // logical sizes: M = B*T*H*W, K = ntaps*C

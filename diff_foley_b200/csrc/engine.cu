@@ -52,14 +52,14 @@ __global__ void pack_vec_kernel(const float* __restrict__ src, float* __restrict
 }
 // OIHW [N,C,3,3] -> [N, tap*C + c]
 __global__ void pack_conv3x3_kernel(const float* __restrict__ src, __half* __restrict__ dst, long N,
-                                    int C) {
+                                    int C, int ldd) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C * 9) return;
   const int tap = (int)(i % 9);
   const long nc = i / 9;
   const int c = (int)(nc % C);
   const long n = nc / C;
-  dst[(n * 9 + tap) * C + c] = __float2half_rn(src[i]);
+  dst[n * ldd + tap * C + c] = __float2half_rn(src[i]);
 }
 // stem OIHW [Cout,Cin,3,3] -> fp32 [(ci*9+tap), Cout]
 __global__ void pack_stem_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout,
@@ -247,7 +247,7 @@ static void reg_vec(dfb_unet* e, const std::string& name, float** dst, int N, lo
 static void reg_conv3(dfb_unet* e, const std::string& name, Lin* lin, int N, int C) {
   reg(e, name, [=](const float* src, const int64_t* s, int nd) -> int {
     if (!shape_is(s, nd, {N, C, 3, 3})) return bad_shape(name);
-    pack_conv3x3_kernel<<<nblk((long)N * C * 9), 256>>>(src, lin->w, N, C);
+    pack_conv3x3_kernel<<<nblk((long)N * C * 9), 256>>>(src, lin->w, N, C, lin->K);
     return cudaGetLastError() == cudaSuccess ? 0 : DFB_E_CUDA;
   });
 }
@@ -402,9 +402,17 @@ static int register_weights(dfb_unet* e) {
     ok &= alloc_norm(e, &r.gn1, r.cin);
     ok &= alloc_norm(e, &r.gn2, r.cout);
     ok &= alloc_lin(e, &r.conv1, r.cout, 9 * r.cin, true);
-    ok &= alloc_lin(e, &r.conv2, r.cout, 9 * r.cout, true);
-    if (r.has_skip) ok &= alloc_lin(e, &r.skip, r.cout, r.cin, true);
+    // the 1x1 skip connection is fused into conv2: its weights are the last cin columns of conv2's
+    // [cout, 9*cout + cin] matrix (second A source of the implicit GEMM), its bias a separate vector
+    ok &= alloc_lin(e, &r.conv2, r.cout, 9 * r.cout + (r.has_skip ? r.cin : 0), true);
     if (!ok) return DFB_E_CUDA;
+    if (r.has_skip) {
+      r.skip.N = r.cout;
+      r.skip.K = r.conv2.K;              // row stride of the view
+      r.skip.w = r.conv2.w + 9 * r.cout;  // column offset of the view
+      r.skip.b = e->dalloc<float>(r.cout);
+      if (!r.skip.b) return DFB_E_CUDA;
+    }
     const std::string& p = r.prefix;
     reg_norm(e, p + ".in_layers.0", &r.gn1);
     reg_conv3(e, p + ".in_layers.2.weight", &r.conv1, r.cout, r.cin);
@@ -581,7 +589,6 @@ struct Builder {
     __half* gn_out = a16[0];
     __half* raw = r.has_skip ? a16[1] : nullptr;
     float* h1 = t32[0];
-    float* sk = t32[1];
     {
       const Norm n = r.gn1;
       const int Bc = B;
@@ -603,12 +610,20 @@ struct Builder {
         return groupnorm_launch(h1, Cc, nullptr, 0, Bc, HW, n.g, n.b, 1e-5f, 1, gn_out, nullptr, s);
       });
     }
-    const float* residual = x0;
     if (r.has_skip) {
-      gemm(raw, r.skip, gemm_geom((int)npix, r.cin), ep_f32(sk, r.cout));
-      residual = sk;
+      // out = conv3x3(h) + b2 + (W_skip x + b_skip): one GEMM over K = 9*cout + cin, the skip bias rides
+      // in as a "per-sample vector" with stride 0 (openai_unetmodel.py:275 + 236-243)
+      IGemmGeom g = conv3x3_geom(B, H, W, r.cout);
+      g.C2 = r.cin;
+      g.A2 = raw;
+      IGemmEpilogue ep = ep_f32(out, r.cout);
+      ep.rowvec = r.skip.b;
+      ep.ld_rowvec = 0;
+      ep.rows_per_sample = HW;
+      gemm(gn_out, r.conv2, g, ep);
+    } else {
+      gemm(gn_out, r.conv2, conv3x3_geom(B, H, W, r.cout), ep_f32(out, r.cout, x0, r.cout));
     }
-    gemm(gn_out, r.conv2, conv3x3_geom(B, H, W, r.cout), ep_f32(out, r.cout, residual, r.cout));
   }
 
   // SpatialTransformer (attention_openai.py:250-261 + 211-215)

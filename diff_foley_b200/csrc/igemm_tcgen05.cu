@@ -43,6 +43,7 @@ struct IGemmKParams {
   int bb, bt, bh, bw;
   int tw, th, tt;  // tiles along W, H, T (tiles along B implied)
   int ntaps, kpt;  // taps, 64-channel k-blocks per tap
+  int kpt2;        // 64-channel k-blocks of the second A source (after the taps), 0 = none
   int8_t dt[9], dh[9], dw[9];
   float* out_f32;
   __half* out_f16;
@@ -97,6 +98,7 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(IGEMM_THREADS, (STAGES <= 4) ? 2 : 1)
 igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                      const __grid_constant__ CUtensorMap tmW,
+                     const __grid_constant__ CUtensorMap tmA2,
                      const __grid_constant__ IGemmKParams p) {
   using L = IGemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -121,7 +123,8 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   const int tb_i = tm;
   const int x0 = tw_i * p.bw, y0 = th_i * p.bh, t0 = tt_i * p.bt, b0 = tb_i * p.bb;
 
-  const int kb_total = p.ntaps * p.kpt;
+  const int kb_taps = p.ntaps * p.kpt;
+  const int kb_total = kb_taps + p.kpt2;
   const int kb0 = (int)(((long)blockIdx.z * kb_total) / p.splits);
   const int kb1 = (int)(((long)(blockIdx.z + 1) * kb_total) / p.splits);
   const int nkb = kb1 - kb0;
@@ -134,6 +137,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
+    if (p.kpt2) tma_prefetch_desc(&tmA2);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -245,15 +249,19 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES;
         const int kb = kb0 + i;
-        const int tap = kb / p.kpt;
-        const int c0 = (kb - tap * p.kpt) * BLOCK_K;
         uint8_t* sa = smem + s * L::STAGE_BYTES;
         if (i >= npre) {  // ring slot reuse: wait for the MMAs that read it, then arm + load W as well
           mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);
           mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
           tma_load_2d(sa + L::A_BYTES, &tmW, &full_bar[s], kb * BLOCK_K, n0);
         }
-        tma_load_5d(sa, &tmA, &full_bar[s], c0, x0 + p.dw[tap], y0 + p.dh[tap], t0 + p.dt[tap], b0);
+        if (kb < kb_taps) {
+          const int tap = kb / p.kpt;
+          const int c0 = (kb - tap * p.kpt) * BLOCK_K;
+          tma_load_5d(sa, &tmA, &full_bar[s], c0, x0 + p.dw[tap], y0 + p.dh[tap], t0 + p.dt[tap], b0);
+        } else {  // second source: same positions, no tap shift
+          tma_load_5d(sa, &tmA2, &full_bar[s], (kb - kb_taps) * BLOCK_K, x0, y0, t0, b0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -636,13 +644,17 @@ int igemm_plan(IGemmPlan* plan, const __half* A, const __half* Wt, int N, const 
   plan->e = e;
   plan->M = g.B * g.T * g.H * g.W;
   plan->N = N;
-  plan->K = g.ntaps * g.C;
+  plan->K = g.ntaps * g.C + g.C2;
   if (splits > 8) splits = 8;  // cluster size limit (portable)
   const bool geglu = (e.act == ACT_GEGLU);
   const int tw = (g.W + g.bw - 1) / g.bw, th = (g.H + g.bh - 1) / g.bh,
             tt = (g.T + g.bt - 1) / g.bt, tb = (g.B + g.bb - 1) / g.bb;
   plan->tiles_m = tw * th * tt * tb;
-  const int kb_total = g.ntaps * (g.C / BLOCK_K);
+  if (g.C2 % BLOCK_K != 0 || (g.C2 > 0 && (g.A2 == nullptr || (reinterpret_cast<uintptr_t>(g.A2) & 15)))) {
+    set_error("igemm: second A source needs a 16-byte aligned pointer and a channel count that is a multiple of 64");
+    return -1;
+  }
+  const int kb_total = g.ntaps * (g.C / BLOCK_K) + g.C2 / BLOCK_K;
   plan->deep = g_force_deep;
   static const bool no_table = getenv("DFB_NO_TUNED") != nullptr;
   const IGemmTuned* tuned = nullptr;
@@ -711,6 +723,16 @@ int igemm_plan(IGemmPlan* plan, const __half* A, const __half* Wt, int N, const 
     uint32_t box[5] = {BLOCK_K, (uint32_t)g.bw, (uint32_t)g.bh, (uint32_t)g.bt, (uint32_t)g.bb};
     int rc = make_tmap_f16(&plan->tmA, A, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
+    plan->tmA2 = plan->tmA;
+    if (g.C2 > 0) {
+      dims[0] = (uint64_t)g.C2;
+      str[0] = (uint64_t)g.C2 * 2;
+      str[1] = str[0] * g.W;
+      str[2] = str[1] * g.H;
+      str[3] = str[2] * g.T;
+      rc = make_tmap_f16(&plan->tmA2, g.A2, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
   }
   {
     uint64_t dims[2] = {(uint64_t)plan->K, (uint64_t)N};
@@ -755,7 +777,7 @@ static int launch_t(const IGemmPlan& plan, const IGemmKParams& kp, cudaStream_t 
   attr[1].val.clusterDim.z = plan.splits;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  DFB_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_tcgen05_kernel<BN, STAGES>, plan.tmA, plan.tmW, kp));
+  DFB_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_tcgen05_kernel<BN, STAGES>, plan.tmA, plan.tmW, plan.tmA2, kp));
   return 0;
 }
 
@@ -771,6 +793,7 @@ int igemm_launch(const IGemmPlan& plan, cudaStream_t stream) {
   kp.tt = (g.T + g.bt - 1) / g.bt;
   kp.ntaps = g.ntaps;
   kp.kpt = g.C / BLOCK_K;
+  kp.kpt2 = g.C2 / BLOCK_K;
   for (int i = 0; i < 9; ++i) { kp.dt[i] = g.dt[i]; kp.dh[i] = g.dh[i]; kp.dw[i] = g.dw[i]; }
   kp.out_f32 = plan.e.out_f32; kp.out_f16 = plan.e.out_f16; kp.ldo = plan.e.ldo;
   kp.bias = plan.e.bias; kp.rowvec = plan.e.rowvec; kp.ld_rowvec = plan.e.ld_rowvec;
@@ -786,7 +809,7 @@ int igemm_launch(const IGemmPlan& plan, cudaStream_t stream) {
   {
     const double out_b = (plan.e.out_f32 ? 4.0 : 0.0) + (plan.e.out_f16 ? 2.0 : 0.0);
     note(g.ntaps == 9 ? "igemm_conv3x3" : "igemm_linear", 2.0 * plan.M * plan.N * plan.K,
-         2.0 * plan.N * plan.K + 2.0 * plan.M * g.C + out_b * plan.M * plan.e.ldo +
+         2.0 * plan.N * plan.K + 2.0 * plan.M * (g.C + g.C2) + out_b * plan.M * plan.e.ldo +
              (plan.e.residual ? 4.0 * plan.M * plan.e.ldo : 0.0),
          plan.M, plan.N, plan.K, plan.splits, plan.tiles_m * plan.tiles_n * plan.splits);
   }

@@ -135,6 +135,13 @@ int dfb_gemm(const void* a_f16_dev, const void* w_f16_dev, int M, int N, int K, 
 int dfb_conv3x3(const void* a_f16_dev, const void* w_f16_dev, int B, int H, int W, int C, int N,
                 const float* bias_dev, const float* rowvec_dev, const float* residual_dev, int act,
                 float* out_f32_dev, void* out_f16_dev, int splits, void* stream);
+/* 3x3 conv (pad 1) over fp16 NHWC `a` [B,H,W,C] plus a 1x1 conv over a second fp16 NHWC tensor `a2`
+ * [B,H,W,C2] accumulated into the same output: weights fp16 [N, 9*C + C2] (the 1x1 weights are the last C2
+ * columns), biases `bias` + `bias2` (either may be NULL).  This is ResBlock.out_layers conv + skip_connection
+ * (openai_unetmodel.py:236-243,275) as ONE implicit GEMM. */
+int dfb_conv3x3_cat(const void* a, const void* a2, int C2, const void* w, int B, int H, int W, int C, int N,
+                    const float* bias, const float* bias2, const float* residual, float* out_f32,
+                    void* out_f16, int splits, void* stream);
 /* "same"-padded stride-1 convolution with an odd (kt,kh,kw) kernel, kt*kh*kw <= 9, over fp16
  * channels-last [B,T,H,W,C] as implicit GEMM (one TMA box per tap); w: fp16 [N, taps*C] with
  * k = ((it*kh + ih)*kw + iw)*C + c.  Covers the CAVP encoders' (1,1,1), (1,3,3), (3,1,1) Conv3d and 3x3

@@ -290,3 +290,30 @@ def test_conv3x3_split_ragged_batch(splits):
             assert rel_l2(out, ref) < 3e-6, (bn, deep)
     finally:
         lib.dfb_debug_igemm_force(0, -1)
+
+
+@pytest.mark.parametrize("B,H,W,C,C2,N,splits", [(2, 16, 64, 320, 640, 320, 0), (2, 4, 16, 128, 64, 192, 3),
+                                                  (3, 2, 8, 64, 128, 64, 1)])
+def test_conv3x3_with_fused_skip(B, H, W, C, C2, N, splits):
+    """conv3x3(a) + conv1x1(a2) + both biases as one implicit GEMM (ResBlock conv2 + skip_connection)."""
+    g = torch.Generator(device="cpu").manual_seed(B + C + C2 + N)
+    a = torch.randn(B, H, W, C, generator=g).to(DEV).half()
+    a2 = torch.randn(B, H, W, C2, generator=g).to(DEV).half()
+    w = (torch.randn(N, C, 3, 3, generator=g) / math.sqrt(9 * C)).to(DEV).half()
+    w2 = (torch.randn(N, C2, generator=g) / math.sqrt(C2)).to(DEV).half()
+    b1 = torch.randn(N, generator=g).to(DEV)
+    b2 = torch.randn(N, generator=g).to(DEV)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = F.conv2d(a.float().permute(0, 3, 1, 2), w.float(), b1, padding=1).permute(0, 2, 3, 1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    ref = ref + a2.float() @ w2.float().t() + b2
+    wp = torch.cat([w.permute(0, 2, 3, 1).reshape(N, 9 * C), w2], dim=1).contiguous()
+    out = torch.full((B, H, W, N), float("nan"), device=DEV, dtype=torch.float32)
+    L.check(L.lib().dfb_conv3x3_cat(L.ptr(a), L.ptr(a2), C2, L.ptr(wp), B, H, W, C, N, L.ptr(b1), L.ptr(b2), None,
+                                    L.ptr(out), None, splits, L.cur_stream()), "dfb_conv3x3_cat")
+    sync()
+    assert torch.isfinite(out).all()
+    assert rel_l2(out, ref) < 3e-6

@@ -54,10 +54,13 @@ def time_candidate(key, b_eff, bn, splits, deep):
     lib.dfb_debug_igemm_force(bn, deep)
     nw = NREP
     ws = [(torch.randn(N, K, device=dev) / K ** 0.5).half() for _ in range(nw)]
+    C2 = 0
     if taps == 9:
-        C = K // 9
+        # conv2 of a ResBlock with a fused 1x1 skip connection: K = 9*N + C2 (never a multiple of 9)
+        C, C2 = (K // 9, 0) if K % 9 == 0 else (N, K - 9 * N)
         H, W = LEVELS[M // b_eff]
         a = torch.randn(b_eff, H, W, C, device=dev).half()
+        a2 = torch.randn(b_eff, H, W, C2, device=dev).half() if C2 else None
     else:
         a = torch.randn(M, K, device=dev).half()
     No = N // 2 if geglu else N
@@ -67,6 +70,9 @@ def time_candidate(key, b_eff, bn, splits, deep):
     o16 = torch.empty(M, No, device=dev, dtype=torch.float16) if geglu else None
 
     def launch(w):
+        if taps == 9 and C2:
+            return lib.dfb_conv3x3_cat(L.ptr(a), L.ptr(a2), C2, L.ptr(w), b_eff, H, W, C, N, L.ptr(bias), None,
+                                       None, L.ptr(o32), None, splits, L.cur_stream())
         if taps == 9:
             return lib.dfb_conv3x3(L.ptr(a), L.ptr(w), b_eff, H, W, C, N, L.ptr(bias), None, L.ptr(res), 0,
                                    L.ptr(o32), None, splits, L.cur_stream())
