@@ -22,8 +22,12 @@
 // The output is fp16 [B*Lq, heads*d], the A operand of the to_out GEMM -- the reference's
 // '(b h) n d -> b n (h d)' rearrange is free.
 //
-// warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = softmax / correction /
-// epilogue (TMEM sub-partition = warp_idx % 4).
+// warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = softmax / correction /
+// epilogue.  The softmax warps are bound by their own instruction stream (one query row per thread,
+// ~6 instructions per score), so TWO warps share each TMEM lane quarter (warp_idx % 4): warps 2..5 take
+// the even 16-key chunks of a block, warps 6..9 the odd ones; the two threads of a row exchange their
+// partial row maxima through shared memory (one 64-thread named barrier per block), keep separate
+// partial row sums, and split the O columns for the rescale and the final normalisation.
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -37,7 +41,7 @@ namespace dfb {
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
 
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;  // 1 TMA + 1 MMA warp + 2 x 4 softmax warps
 constexpr int ATT_BM = 128;  // queries per CTA
 
 struct AttParams {
@@ -63,7 +67,7 @@ __device__ __forceinline__ void tmem_st_wait() {
 // smem carve-up (bytes), all tiles in the [chunk][row][8 halves] layout
 struct AttSmem {
   int q_bytes, kv_tile_bytes, p_bytes;
-  int off_q, off_k[2], off_v[2], off_p[2], off_bar, total;
+  int off_q, off_k[2], off_v[2], off_p[2], off_bar, off_xch, total;
 };
 __host__ __device__ inline AttSmem att_smem_layout(int dpad, int KB) {
   AttSmem s;
@@ -75,7 +79,8 @@ __host__ __device__ inline AttSmem att_smem_layout(int dpad, int KB) {
   for (int i = 0; i < 2; ++i) { s.off_k[i] = o; o += s.kv_tile_bytes; s.off_v[i] = o; o += s.kv_tile_bytes; }
   for (int i = 0; i < 2; ++i) { s.off_p[i] = o; o += s.p_bytes; }
   s.off_bar = (o + 15) & ~15;
-  s.total = s.off_bar + 16 * 8 + 16;
+  s.off_xch = s.off_bar + 16 * 8 + 16;            // float [2 parities][2 halves][128 rows] maxima + [2][128] sums
+  s.total = s.off_xch + (4 + 2) * ATT_BM * 4;
   return s;
 }
 
@@ -118,7 +123,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         mbar_init(&kv_full[i], 1);
         mbar_init(&kv_empty[i], 1);
         mbar_init(&s_full[i], 1);
-        mbar_init(&p_full[i], 128);
+        mbar_init(&p_full[i], 256);
       }
       mbar_init(pv_done, 1);
       fence_mbar_init();
@@ -140,19 +145,18 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   if (warp == 0) {
     // ======================================================================== TMA producer
     if (lane == 0) {
-      // one 2-D box (8 halves x rows) per 16-byte chunk: chunk c lands at tile + c*rows*16
-      const int nch = p.dpad >> 3, col0 = h * p.dpad;
+      // ONE 3-D box (8 halves x rows x chunks) per tile: the tensor map orders the dims as (8 halves,
+      // row, 16-byte chunk of the row), so the box lands as [chunk][row][8 halves] -- chunk c at
+      // tile + c*rows*16 -- with a single TMA operation instead of one per chunk
+      const int ch0 = (h * p.dpad) >> 3;
       mbar_expect_tx(q_full, L.q_bytes);
-      for (int c = 0; c < nch; ++c)
-        tma_load_2d(smem + L.off_q + c * (ATT_BM * 16), &tmQ, q_full, col0 + 8 * c, b * p.Lq + q0);
+      tma_load_3d(smem + L.off_q, &tmQ, q_full, 0, b * p.Lq + q0, ch0);
       for (int j = 0; j < nb; ++j) {
         const int s = j & 1;
         mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(&kv_full[s], 2 * L.kv_tile_bytes);
-        for (int c = 0; c < nch; ++c) {
-          tma_load_2d(smem + L.off_k[s] + c * (KB * 16), &tmK, &kv_full[s], col0 + 8 * c, b * p.Lk + j * KB);
-          tma_load_2d(smem + L.off_v[s] + c * (KB * 16), &tmV, &kv_full[s], col0 + 8 * c, b * p.Lk + j * KB);
-        }
+        tma_load_3d(smem + L.off_k[s], &tmK, &kv_full[s], 0, b * p.Lk + j * KB, ch0);
+        tma_load_3d(smem + L.off_v[s], &tmV, &kv_full[s], 0, b * p.Lk + j * KB, ch0);
       }
     }
   } else if (warp == 1) {
@@ -207,43 +211,50 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   } else {
     // ============================================================ softmax / correction / epilogue
     const int sub = warp & 3;
-    const int r = sub * 32 + lane;  // query row within the tile == TMEM lane
+    const int half = (warp - 2) >> 2;   // 0: even 16-key chunks of a block, 1: odd ones
+    const int r = sub * 32 + lane;      // query row within the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(sub * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;
+    float* xmax = reinterpret_cast<float*>(smem + L.off_xch);   // [parity][half][row]
+    float* xsum = xmax + 4 * ATT_BM;                             // [half][row]
+    constexpr int NQH = NQ / 2;         // chunks per thread per block
+    float m_run = -INFINITY, l_run = 0.f;  // l_run: this thread's share of the row sum
     for (int j = 0; j < nb; ++j) {
       const int s = j & 1;
       mbar_wait(&s_full[s], (j >> 1) & 1);
       tc_fence_after();
       const int kvalid = min(KB, p.Lk - j * KB);  // keys of this block that exist
-      float mx, m_new, alpha, psum = 0.f;
       uint8_t* prow = smem + L.off_p[s] + r * 16;
-      if constexpr (NQ <= 4) {
-      // ---- one TMEM pass: the whole S row of this block (KB <= 64 values) into registers
-      uint32_t raw[NQ][16];
+      // ---- one TMEM pass: this thread's chunks of the S row into registers
+      uint32_t raw[NQH][16];
 #pragma unroll
-      for (int q = 0; q < NQ; ++q)
-        if (q * 16 < KB) tmem_ld_32x16(tm_s[s] + lane_off + q * 16, raw[q]);
+      for (int q = 0; q < NQH; ++q)
+        if ((2 * q + half) * 16 < KB) tmem_ld_32x16(tm_s[s] + lane_off + (2 * q + half) * 16, raw[q]);
       tmem_ld_wait();
-      mx = -INFINITY;
+      float mx = -INFINITY;
 #pragma unroll
-      for (int q = 0; q < NQ; ++q)
-        if (q * 16 < KB) {
+      for (int q = 0; q < NQH; ++q)
+        if ((2 * q + half) * 16 < KB) {
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (q * 16 + i < kvalid) mx = fmaxf(mx, __uint_as_float(raw[q][i]));
+            if ((2 * q + half) * 16 + i < kvalid) mx = fmaxf(mx, __uint_as_float(raw[q][i]));
         }
-      m_new = fmaxf(m_run, mx * p.scale_log2);
-      alpha = exp2f(m_run - m_new);  // 0 on the first block (m_run = -inf)
-      // ---- p = exp2(s*scale - m), row sum, fp16 P tile in the canonical K-major layout
-
+      // ---- row maximum across the two threads of this row
+      xmax[(s * 2 + half) * ATT_BM + r] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + sub) : "memory");
+      mx = fmaxf(mx, xmax[(s * 2 + (half ^ 1)) * ATT_BM + r]);
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float alpha = exp2f(m_run - m_new);  // 0 on the first block (m_run = -inf)
+      // ---- p = exp2(s*scale - m), partial row sum, fp16 P tile in the canonical K-major layout
+      float psum = 0.f;
 #pragma unroll
-      for (int q = 0; q < NQ; ++q)
-        if (q * 16 < KB) {
+      for (int q = 0; q < NQH; ++q)
+        if ((2 * q + half) * 16 < KB) {
+          const int c0 = (2 * q + half) * 16;
           float e[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float v = exp2f(fmaf(__uint_as_float(raw[q][i]), p.scale_log2, -m_new));
-            e[i] = (q * 16 + i < kvalid) ? v : 0.f;
+            e[i] = (c0 + i < kvalid) ? v : 0.f;
             psum += e[i];
           }
 #pragma unroll
@@ -255,65 +266,25 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             uint4 u;
             u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
             u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(prow + (q * 2 + g) * (ATT_BM * 16)) = u;
+            *reinterpret_cast<uint4*>(prow + ((c0 >> 3) + g) * (ATT_BM * 16)) = u;
           }
         }
-      } else {
-        // wide key blocks: two rolled TMEM passes (max, then exp) keep the code small -- this kernel
-        // starts with a cold instruction cache on every launch
-      mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < KB; c += 16) {
-        uint32_t rw[16];
-        tmem_ld_32x16(tm_s[s] + lane_off + c, rw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (c + i < kvalid) mx = fmaxf(mx, __uint_as_float(rw[i]));
-      }
-      m_new = fmaxf(m_run, mx * p.scale_log2);
-      alpha = exp2f(m_run - m_new);  // 0 on the first block (m_run = -inf)
-#pragma unroll 1
-      for (int c = 0; c < KB; c += 16) {
-        uint32_t rw[16];
-        tmem_ld_32x16(tm_s[s] + lane_off + c, rw);
-        tmem_ld_wait();
-        float e[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float v = exp2f(fmaf(__uint_as_float(rw[i]), p.scale_log2, -m_new));
-          e[i] = (c + i < kvalid) ? v : 0.f;
-          psum += e[i];
-        }
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          __half2 h0 = __floats2half2_rn(e[8 * g + 0], e[8 * g + 1]);
-          __half2 h1 = __floats2half2_rn(e[8 * g + 2], e[8 * g + 3]);
-          __half2 h2 = __floats2half2_rn(e[8 * g + 4], e[8 * g + 5]);
-          __half2 h3 = __floats2half2_rn(e[8 * g + 6], e[8 * g + 7]);
-          uint4 u;
-          u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-          u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-          *reinterpret_cast<uint4*>(prow + ((c >> 3) + g) * (ATT_BM * 16)) = u;
-        }
-      }
-      }
       l_run = l_run * alpha + psum;
       m_run = m_new;
       fence_proxy_async_smem();  // generic-proxy P stores -> visible to the tensor core (async proxy)
-      // ---- correction: O *= alpha, in TMEM, once the previous P V has landed
+      // ---- correction: O *= alpha, in TMEM, once the previous P V has landed (columns split by half)
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);
         tc_fence_after();
         if (__any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll 1
-          for (int c = 0; c < p.dpad; c += 16) {
-            uint32_t raw[16];
-            tmem_ld_32x16(tm_o + lane_off + c, raw);
+          for (int c = half * 16; c < p.dpad; c += 32) {
+            uint32_t rw[16];
+            tmem_ld_32x16(tm_o + lane_off + c, rw);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
-            tmem_st_32x16(tm_o + lane_off + c, raw);
+            for (int i = 0; i < 16; ++i) rw[i] = __float_as_uint(__uint_as_float(rw[i]) * alpha);
+            tmem_st_32x16(tm_o + lane_off + c, rw);
           }
           tmem_st_wait();
         }
@@ -321,23 +292,25 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tc_fence_before();
       mbar_arrive(&p_full[s]);
     }
-    // ---- epilogue: O / l -> fp16 [row, h*d + c]
+    // ---- epilogue: O / l -> fp16 [row, h*d + c]; the row sum is the two threads' shares
+    xsum[half * ATT_BM + r] = l_run;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + sub) : "memory");
+    const float inv = 1.f / (l_run + xsum[(half ^ 1) * ATT_BM + r]);
     mbar_wait(pv_done, (nb - 1) & 1);
     tc_fence_after();
-    const float inv = 1.f / l_run;
     const bool row_ok = (q0 + r) < p.Lq;
     __half* orow = p.out + ((size_t)b * p.Lq + q0 + r) * p.ldo + h * p.d;
 #pragma unroll 1
-    for (int c = 0; c < p.dpad; c += 16) {
-      uint32_t raw[16];
-      tmem_ld_32x16(tm_o + lane_off + c, raw);
+    for (int c = half * 16; c < p.dpad; c += 32) {
+      uint32_t rw[16];
+      tmem_ld_32x16(tm_o + lane_off + c, rw);
       tmem_ld_wait();
       if (row_ok) {
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
           if (c + i < p.d)
             *reinterpret_cast<__half2*>(orow + c + i) =
-                __floats2half2_rn(__uint_as_float(raw[i]) * inv, __uint_as_float(raw[i + 1]) * inv);
+                __floats2half2_rn(__uint_as_float(rw[i]) * inv, __uint_as_float(rw[i + 1]) * inv);
         }
       }
     }
@@ -374,11 +347,12 @@ static int get_tmap(CUtensorMap* out, const __half* base, int ld, long rows, int
   std::lock_guard<std::mutex> lk(g_tmap_mu);
   auto it = g_tmaps.find(key);
   if (it != g_tmaps.end()) { *out = it->second; return 0; }
-  // plain 2-D view [rows, ld] fp16; box = 8 halves (one 16-byte chunk) x box_rows
-  uint64_t dims[2] = {(uint64_t)ld, (uint64_t)rows};
-  uint64_t strides[1] = {(uint64_t)ld * 2};
-  uint32_t box[2] = {8, (uint32_t)box_rows};
-  int rc = make_tmap_f16(out, base, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+  // 3-D view of the row-major [rows, ld] fp16 matrix: (8 halves, row, 16-byte chunk of the row); box =
+  // 8 halves x box_rows x (dpad / 8) chunks
+  uint64_t dims[3] = {8, (uint64_t)rows, (uint64_t)(ld / 8)};
+  uint64_t strides[2] = {(uint64_t)ld * 2, 16};
+  uint32_t box[3] = {8, (uint32_t)box_rows, (uint32_t)(dpad / 8)};
+  int rc = make_tmap_f16(out, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
   if (g_tmaps.size() > 4096) g_tmaps.clear();
   g_tmaps[key] = *out;
