@@ -145,18 +145,19 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   if (warp == 0) {
     // ======================================================================== TMA producer
     if (lane == 0) {
-      // ONE 3-D box (8 halves x rows x chunks) per tile: the tensor map orders the dims as (8 halves,
-      // row, 16-byte chunk of the row), so the box lands as [chunk][row][8 halves] -- chunk c at
-      // tile + c*rows*16 -- with a single TMA operation instead of one per chunk
-      const int ch0 = (h * p.dpad) >> 3;
+      // one 2-D box (8 halves x rows) per 16-byte chunk: chunk c lands at tile + c*rows*16
+      const int nch = p.dpad >> 3, col0 = h * p.dpad;
       mbar_expect_tx(q_full, L.q_bytes);
-      tma_load_3d(smem + L.off_q, &tmQ, q_full, 0, b * p.Lq + q0, ch0);
+      for (int c = 0; c < nch; ++c)
+        tma_load_2d(smem + L.off_q + c * (ATT_BM * 16), &tmQ, q_full, col0 + 8 * c, b * p.Lq + q0);
       for (int j = 0; j < nb; ++j) {
         const int s = j & 1;
         mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(&kv_full[s], 2 * L.kv_tile_bytes);
-        tma_load_3d(smem + L.off_k[s], &tmK, &kv_full[s], 0, b * p.Lk + j * KB, ch0);
-        tma_load_3d(smem + L.off_v[s], &tmV, &kv_full[s], 0, b * p.Lk + j * KB, ch0);
+        for (int c = 0; c < nch; ++c) {
+          tma_load_2d(smem + L.off_k[s] + c * (KB * 16), &tmK, &kv_full[s], col0 + 8 * c, b * p.Lk + j * KB);
+          tma_load_2d(smem + L.off_v[s] + c * (KB * 16), &tmV, &kv_full[s], col0 + 8 * c, b * p.Lk + j * KB);
+        }
       }
     }
   } else if (warp == 1) {
@@ -347,12 +348,11 @@ static int get_tmap(CUtensorMap* out, const __half* base, int ld, long rows, int
   std::lock_guard<std::mutex> lk(g_tmap_mu);
   auto it = g_tmaps.find(key);
   if (it != g_tmaps.end()) { *out = it->second; return 0; }
-  // 3-D view of the row-major [rows, ld] fp16 matrix: (8 halves, row, 16-byte chunk of the row); box =
-  // 8 halves x box_rows x (dpad / 8) chunks
-  uint64_t dims[3] = {8, (uint64_t)rows, (uint64_t)(ld / 8)};
-  uint64_t strides[2] = {(uint64_t)ld * 2, 16};
-  uint32_t box[3] = {8, (uint32_t)box_rows, (uint32_t)(dpad / 8)};
-  int rc = make_tmap_f16(out, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+  // plain 2-D view [rows, ld] fp16; box = 8 halves (one 16-byte chunk) x box_rows
+  uint64_t dims[2] = {(uint64_t)ld, (uint64_t)rows};
+  uint64_t strides[1] = {(uint64_t)ld * 2};
+  uint32_t box[2] = {8, (uint32_t)box_rows};
+  int rc = make_tmap_f16(out, base, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
   if (g_tmaps.size() > 4096) g_tmaps.clear();
   g_tmaps[key] = *out;
