@@ -68,6 +68,7 @@ SIGNATURES = {
     "dfb_im2col_f16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dfb_pool2d_f16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dfb_groupnorm": (_i, [_fp, _i, _fp, _i, _i, _i, _fp, _fp, _f, _i, _vp, _vp, _vp]),
+    "dfb_softmax_rows": (_i, [_fp, _i, _i, _f, _vp, _vp]),
     "dfb_layernorm": (_i, [_fp, _i, _i, _fp, _fp, _f, _vp, _vp]),
     "dfb_attention": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "dfb_temb": (_i, [_vp, _i, _i, _i, _vp, _vp]),

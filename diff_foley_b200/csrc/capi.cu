@@ -148,6 +148,10 @@ int dfb_layernorm(const float* src, int rows, int C, const float* gamma, const f
   return layernorm_launch(src, rows, C, gamma, beta, eps, (__half*)out, (cudaStream_t)stream);
 }
 
+int dfb_softmax_rows(const float* src, int rows, int n, float scale, void* out, void* stream) {
+  return softmax_rows_launch(src, rows, n, scale, (__half*)out, (cudaStream_t)stream);
+}
+
 int dfb_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
                   int ldo, int B, int heads, int Lq, int Lk, int d, int dpad, float scale, void* stream) {
   int r = kernels_init();

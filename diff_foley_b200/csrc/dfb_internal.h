@@ -150,6 +150,9 @@ int groupnorm_launch(const float* src0, int C0, const float* src1, int C1, int B
 int layernorm_launch(const float* src, int rows, int C, const float* gamma, const float* beta,
                      float eps, __half* out, cudaStream_t stream);
 
+// softmax(scale * x) over the rows of fp32 [rows, n] -> fp16 (n <= 2048)
+int softmax_rows_launch(const float* src, int rows, int n, float scale, __half* out, cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------- attention
 // q: fp16 rows [B*Lq, ldq] (head h at columns h*dpad), k/v likewise with Lk rows per sample.
 // out: fp16 [B*Lq, ldo], head h at columns h*d (un-padded).

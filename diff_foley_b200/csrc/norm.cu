@@ -147,6 +147,107 @@ groupnorm_kernel(const float* __restrict__ src0, int C0, const float* __restrict
 }
 
 
+// ---- slabs too large for one cluster's registers (the first-stage decoder: 128..512 channels at up to
+// 128x512 pixels, model.py:557-663 of the reference's stage1_autoencoder).  Two kernels over pixel
+// chunks: (1) every CTA reduces its chunk about the slab's pivot and writes (s1, s2) to a slot of a small
+// workspace -- no atomics, the slots are summed in order by (2), which re-reads its chunk, normalises and
+// writes fp16.  grid = (chunks, 32 groups, B).
+constexpr int GNB_THREADS = 256;
+constexpr int GNB_CHUNK_PX = 1024;  // pixels per CTA
+static float* g_gn_ws = nullptr;    // [B][32][chunks][2]
+constexpr size_t GN_WS_FLOATS = 1 << 18;
+
+__device__ __forceinline__ const float* gn_src(const float* src0, int C0, const float* src1, int C1, size_t pix,
+                                               int c) {
+  return (c < C0) ? src0 + pix * C0 + c : src1 + pix * C1 + (c - C0);
+}
+
+__global__ void __launch_bounds__(GNB_THREADS)
+groupnorm_big_stats_kernel(const float* __restrict__ src0, int C0, const float* __restrict__ src1, int C1,
+                           int HW, float* __restrict__ ws) {
+  __shared__ float red[GNB_THREADS / 32], red2[GNB_THREADS / 32];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int C = C0 + C1, cpg = C / 32, hp = cpg >> 1;
+  const int chunk = blockIdx.x, g = blockIdx.y, b = blockIdx.z, cbase = g * cpg;
+  const int px0 = chunk * GNB_CHUNK_PX, npx = min(GNB_CHUNK_PX, HW - px0);
+  const float piv = *gn_src(src0, C0, src1, C1, (size_t)b * HW, cbase);
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < npx * hp; i += GNB_THREADS) {
+    const int px = px0 + i / hp, c = cbase + 2 * (i % hp);
+    const float2 v = *reinterpret_cast<const float2*>(gn_src(src0, C0, src1, C1, (size_t)b * HW + px, c));
+    const float dx = v.x - piv, dy = v.y - piv;
+    s1 += dx + dy;
+    s2 += dx * dx + dy * dy;
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[warp] = s1; red2[warp] = s2; }
+  __syncthreads();
+  if (warp == 0) {
+    s1 = warp_sum(lane < GNB_THREADS / 32 ? red[lane] : 0.f);
+    s2 = warp_sum(lane < GNB_THREADS / 32 ? red2[lane] : 0.f);
+    if (lane == 0) {
+      float* slot = ws + (((size_t)b * 32 + g) * gridDim.x + chunk) * 2;
+      slot[0] = s1;
+      slot[1] = s2;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GNB_THREADS)
+groupnorm_big_apply_kernel(const float* __restrict__ src0, int C0, const float* __restrict__ src1, int C1,
+                           int HW, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                           int silu, const float* __restrict__ ws, __half* __restrict__ out,
+                           __half* __restrict__ raw_out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int C = C0 + C1, cpg = C / 32, hp = cpg >> 1;
+  const int chunk = blockIdx.x, g = blockIdx.y, b = blockIdx.z, cbase = g * cpg;
+  const int px0 = chunk * GNB_CHUNK_PX, npx = min(GNB_CHUNK_PX, HW - px0);
+  const float piv = *gn_src(src0, C0, src1, C1, (size_t)b * HW, cbase);
+  float s1 = 0.f, s2 = 0.f;
+  const float* slots = ws + ((size_t)b * 32 + g) * gridDim.x * 2;
+  for (int k = 0; k < (int)gridDim.x; ++k) { s1 += slots[2 * k]; s2 += slots[2 * k + 1]; }  // in order
+  const float inv_n = 1.f / ((float)HW * (float)cpg);
+  const float dm = s1 * inv_n, mean = piv + dm;
+  const float rstd = rsqrtf(fmaxf(s2 * inv_n - dm * dm, 0.f) + eps);
+  for (int i = threadIdx.x; i < npx * hp; i += GNB_THREADS) {
+    const int px = px0 + i / hp, c = cbase + 2 * (i % hp);
+    const float2 v = *reinterpret_cast<const float2*>(gn_src(src0, C0, src1, C1, (size_t)b * HW + px, c));
+    float y0 = (v.x - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+    float y1 = (v.y - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
+    if (silu) {
+      y0 = y0 / (1.f + expf(-y0));
+      y1 = y1 / (1.f + expf(-y1));
+    }
+    const size_t o = ((size_t)b * HW + px) * C + c;
+    *reinterpret_cast<__half2*>(out + o) = __floats2half2_rn(y0, y1);
+    if (raw_out != nullptr) *reinterpret_cast<__half2*>(raw_out + o) = __floats2half2_rn(v.x, v.y);
+  }
+}
+
+static int groupnorm_big_launch(const float* src0, int C0, const float* src1, int C1, int B, int HW,
+                                const float* gamma, const float* beta, float eps, int silu, __half* out,
+                                __half* raw_out, cudaStream_t stream) {
+  const int chunks = (HW + GNB_CHUNK_PX - 1) / GNB_CHUNK_PX;
+  if ((size_t)B * 32 * chunks * 2 > GN_WS_FLOATS) {
+    set_error("groupnorm: batch x pixels too large for the statistics workspace");
+    return -1;
+  }
+  if (g_gn_ws == nullptr) DFB_CUDA_OK(cudaMalloc(&g_gn_ws, GN_WS_FLOATS * sizeof(float)));
+  const int C = C0 + C1;
+  note("groupnorm", 0.0, (double)B * HW * C * (8.0 + 2.0 + (raw_out ? 2.0 : 0.0)), B * HW, C, 0, 1, 32 * B * chunks);
+  const dim3 grid(chunks, 32, B);
+  DFB_CUDA_OK(launch_pdl(groupnorm_big_stats_kernel, grid, dim3(GNB_THREADS), 0, stream, src0, C0, src1, C1, HW,
+                         g_gn_ws));
+  DFB_CUDA_OK(launch_pdl(groupnorm_big_apply_kernel, grid, dim3(GNB_THREADS), 0, stream, src0, C0, src1, C1, HW,
+                         gamma, beta, eps, silu, (const float*)g_gn_ws, out, raw_out));
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int groupnorm_launch(const float* src0, int C0, const float* src1, int C1, int B, int HW,
                      const float* gamma, const float* beta, float eps, int silu, __half* out,
                      __half* raw_out, cudaStream_t stream) {
@@ -161,10 +262,8 @@ int groupnorm_launch(const float* src0, int C0, const float* src1, int C1, int B
   int P = (int)((pairs + cap - 1) / cap);
   // spread a slab over a few SMs when there are enough pixels to split (latency, not capacity)
   if (HW >= 1024) P = std::max(P, 4); else if (HW >= 256) P = std::max(P, 2);
-  if (P > 8) {
-    set_error("groupnorm: group slab of " + std::to_string(pairs * 2) + " elements is too large");
-    return -1;
-  }
+  if (P > 8)  // slab beyond one cluster's registers: statistics + apply kernels over pixel chunks
+    return groupnorm_big_launch(src0, C0, src1, C1, B, HW, gamma, beta, eps, silu, out, raw_out, stream);
   note("groupnorm", 0.0, (double)B * HW * C * (4.0 + 2.0 + (raw_out ? 2.0 : 0.0)), B * HW, C, 0, 1, 32 * B * P);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(P, 32, B);
@@ -258,6 +357,67 @@ int layernorm_launch(const float* src, int rows, int C, const float* gamma, cons
   note("layernorm", 0.0, (double)rows * C * 6.0, rows, C, 0, 1, nblk);
   DFB_CUDA_OK(launch_pdl(layernorm_kernel, dim3(nblk), dim3(warps * 32), 0, stream, src, rows, C, gamma, beta, eps, out,
                          trace_record()));
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// softmax(scale * x) over the rows of fp32 [rows, n] -> fp16 (the first-stage decoder's single-head
+// 512-wide attention, model.py:245-300: its head dim exceeds the fused attention kernel's TMEM budget, so
+// q k^T and P v run as plain GEMMs around this kernel).  One warp per row, the row in registers.
+constexpr int SM_MAXV = 16;  // float4 per lane: n <= 2048
+__global__ void __launch_bounds__(128)
+softmax_rows_kernel(const float* __restrict__ src, int rows, int n, float scale, __half* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* x = reinterpret_cast<const float4*>(src + (size_t)row * n);
+  const int n4 = n >> 2;
+  float4 v[SM_MAXV];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < SM_MAXV; ++k) {
+    const int i = lane + 32 * k;
+    if (i < n4) {
+      v[k] = x[i];
+      mx = fmaxf(mx, fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w)));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float sl = scale * 1.4426950408889634f, ml = mx * sl;
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < SM_MAXV; ++k) {
+    if (lane + 32 * k < n4) {
+      v[k].x = exp2f(fmaf(v[k].x, sl, -ml)); v[k].y = exp2f(fmaf(v[k].y, sl, -ml));
+      v[k].z = exp2f(fmaf(v[k].z, sl, -ml)); v[k].w = exp2f(fmaf(v[k].w, sl, -ml));
+      sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+  }
+  const float inv = 1.f / warp_sum(sum);
+  __half* o = out + (size_t)row * n;
+#pragma unroll
+  for (int k = 0; k < SM_MAXV; ++k) {
+    const int i = lane + 32 * k;
+    if (i < n4) {
+      const __half2 h0 = __floats2half2_rn(v[k].x * inv, v[k].y * inv);
+      const __half2 h1 = __floats2half2_rn(v[k].z * inv, v[k].w * inv);
+      uint2 u;
+      u.x = *reinterpret_cast<const uint32_t*>(&h0);
+      u.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(o + 4 * i) = u;
+    }
+  }
+}
+
+int softmax_rows_launch(const float* src, int rows, int n, float scale, __half* out, cudaStream_t stream) {
+  if (n % 4 != 0 || n > 128 * SM_MAXV || rows < 1) {
+    set_error("softmax_rows: n must be a multiple of 4 and <= 2048");
+    return -1;
+  }
+  note("softmax", 0.0, (double)rows * n * 6.0, rows, n, 0, 1, (rows + 3) / 4);
+  DFB_CUDA_OK(launch_pdl(softmax_rows_kernel, dim3((rows + 3) / 4), dim3(128), 0, stream, src, rows, n, scale, out));
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
 }

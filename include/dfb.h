@@ -157,10 +157,14 @@ int dfb_im2col_f16(const void* src_dev, void* dst_dev, int NI, int H, int W, int
 /* max (is_max=1) or average pooling on fp16 channels-last images */
 int dfb_pool2d_f16(const void* src_dev, void* dst_dev, int NI, int H, int W, int C, int kh, int kw, int sh,
                    int sw, int ph, int pw, int is_max, void* stream);
-/* GroupNorm(32) (+SiLU) over concat(src0, src1) channels-last fp32 -> fp16 (util.py:214-216) */
+/* GroupNorm(32) (+SiLU) over concat(src0, src1) channels-last fp32 -> fp16 (util.py:214-216); group slabs
+ * beyond 64 K elements (the first-stage decoder's upper levels) take a two-kernel statistics + apply path */
 int dfb_groupnorm(const float* src0_dev, int C0, const float* src1_dev, int C1, int B, int HW,
                   const float* gamma_dev, const float* beta_dev, float eps, int silu, void* out_f16_dev,
                   void* raw_f16_dev, void* stream);
+/* softmax(scale * x) over the rows of fp32 [rows, n] (n % 4 == 0, n <= 2048) -> fp16: the first-stage
+ * decoder's 512-wide single-head attention (stage1_autoencoder/model.py:245-300) between two dfb_gemm calls */
+int dfb_softmax_rows(const float* src_dev, int rows, int n, float scale, void* out_f16_dev, void* stream);
 int dfb_layernorm(const float* src_dev, int rows, int C, const float* gamma_dev, const float* beta_dev,
                   float eps, void* out_f16_dev, void* stream);
 /* softmax(q k^T scale) v per (sample, head) (attention_openai.py:170-193); fp16 in/out */

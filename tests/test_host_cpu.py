@@ -70,3 +70,16 @@ def test_sampler_schedule_equals_oracle():
         assert np.array_equal(s._steps[k], c[k]), k
     with pytest.raises(NotImplementedError):
         s.make_schedule(25, ddim_eta=1.0)
+
+
+def test_vae_decoder_state_dict_matches_reference_keys():
+    """AutoencoderKLDecoderB200 exposes the decode half of the reference AutoencoderKL's parameters."""
+    from diff_foley_b200.vae import AutoencoderKLDecoderB200
+    from oracle import vae_oracle
+    with torch.device("meta"):
+        m = AutoencoderKLDecoderB200()
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    want = dict(vae_oracle.decoder_param_shapes())
+    assert got == want
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        AutoencoderKLDecoderB200().decode(torch.zeros(1, 4, 16, 64))

@@ -317,3 +317,35 @@ def test_conv3x3_with_fused_skip(B, H, W, C, C2, N, splits):
     sync()
     assert torch.isfinite(out).all()
     assert rel_l2(out, ref) < 3e-6
+
+
+@pytest.mark.parametrize("C,HW,B", [(128, 65536, 1), (256, 16384, 2), (512, 16384, 1)])
+def test_groupnorm_big_slab(C, HW, B):
+    """Group slabs beyond one cluster's registers (first-stage decoder levels): statistics + apply path."""
+    g = torch.Generator(device="cpu").manual_seed(C + HW)
+    x = (torch.randn(B, HW, C, generator=g) * 1.7 + 0.4).to(DEV)
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(C, generator=g)).to(DEV)
+    out = torch.empty(B, HW, C, device=DEV, dtype=torch.float16)
+    raw = torch.empty_like(out)
+    L.check(L.lib().dfb_groupnorm(L.ptr(x), C, None, 0, B, HW, L.ptr(gamma), L.ptr(beta), 1e-6, 1, L.ptr(out),
+                                  L.ptr(raw), L.cur_stream()), "dfb_groupnorm")
+    sync()
+    ref = F.silu(F.group_norm(x.permute(0, 2, 1), 32, gamma, beta, 1e-6)).permute(0, 2, 1)
+    assert rel_l2(out.float(), ref) < 1e-3  # fp16 output rounding
+    assert rel_l2(raw.float(), x) < 1e-3
+    again = torch.empty_like(out)
+    L.check(L.lib().dfb_groupnorm(L.ptr(x), C, None, 0, B, HW, L.ptr(gamma), L.ptr(beta), 1e-6, 1, L.ptr(again),
+                                  None, L.cur_stream()), "dfb_groupnorm")
+    sync()
+    assert torch.equal(out, again)
+
+
+def test_softmax_rows():
+    g = torch.Generator(device="cpu").manual_seed(9)
+    x = (torch.randn(1024, 1024, generator=g) * 30).to(DEV)
+    out = torch.empty(1024, 1024, device=DEV, dtype=torch.float16)
+    L.check(L.lib().dfb_softmax_rows(L.ptr(x), 1024, 1024, 512 ** -0.5, L.ptr(out), L.cur_stream()), "softmax")
+    sync()
+    ref = torch.softmax(x * 512 ** -0.5, dim=1)
+    assert rel_l2(out.float(), ref) < 1e-3
