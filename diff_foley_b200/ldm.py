@@ -59,12 +59,22 @@ class DiffusionWrapperB200(nn.Module):
 
 class LatentDiffusionB200(nn.Module):
     def __init__(self, unet_params, cond_stage_params=None, linear_start=0.00085, linear_end=0.0120,
-                 timesteps=1000, channels=4, scale_factor=0.18215, conditioning_key="crossattn", **ignored):
+                 timesteps=1000, channels=4, scale_factor=0.18215, conditioning_key="crossattn",
+                 first_stage_params=None, **ignored):
         super().__init__()
         unet = unet_params if isinstance(unet_params, nn.Module) else UNetModelB200(**unet_params)
         self.model = DiffusionWrapperB200(unet, conditioning_key)
         cs = dict(origin_dim=512, embed_dim=768, seq_len=40) if cond_stage_params is None else cond_stage_params
         self.cond_stage_model = VideoFeatEncoderPosembed(**cs)
+        # first stage (decode half only): built when asked for -- `first_stage_params` = the reference's
+        # first_stage_config.params (Stage2_LDM.yaml:38-59) or True for its defaults
+        self.first_stage_model = None
+        if first_stage_params:
+            from .vae import AutoencoderKLDecoderB200
+            fs = {} if first_stage_params is True else dict(first_stage_params)
+            self.first_stage_model = AutoencoderKLDecoderB200(ddconfig=fs.get("ddconfig"),
+                                                              embed_dim=fs.get("embed_dim", 4),
+                                                              scale_factor=scale_factor)
         self.channels = channels
         self.scale_factor = scale_factor
         self.parameterization = "eps"
@@ -83,6 +93,13 @@ class LatentDiffusionB200(nn.Module):
 
     def get_learned_conditioning(self, c):
         return self.cond_stage_model(c)
+
+    @torch.no_grad()
+    def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):
+        """ddpm.py:739-797: `1/scale_factor * z` -> AutoencoderKL.decode -> [B,3,128,512] (mel = channel 0)."""
+        if self.first_stage_model is None:
+            raise RuntimeError("LatentDiffusionB200 was built without first_stage_params")
+        return self.first_stage_model.decode(z / self.scale_factor)
 
     def apply_model(self, x_noisy, t, cond, return_ids=False):
         if not isinstance(cond, list):

@@ -107,6 +107,15 @@ def test_fused_ddim_matches_reference_sampler(name, cfg):
         err_mel = rel_l2(mel, gv["mel"])
         print(f"[parity] {name}: DECODED MEL rel-L2 after DDIM-25 = {err_mel:.3e}   (target <= 1e-3)")
         assert err_mel < 1e-3
+        # and the fully native pipeline: our latent through OUR first-stage decoder (diff_foley_b200/vae.py)
+        # against the reference latent through the reference's AutoencoderKL.decode
+        from diff_foley_b200.vae import AutoencoderKLDecoderB200
+        vae = AutoencoderKLDecoderB200()
+        vae.load_state_dict(vsd)
+        mel_native = vae.cuda().decode_first_stage(samples)[:, 0]
+        err_native = rel_l2(mel_native, gv["mel"])
+        print(f"[parity] {name}: DECODED MEL, native sampler + native decoder = {err_native:.3e}")
+        assert err_native < 2e-3
     # the host-loop path (apply_model + dfb_ddim_step) must agree with the fused graph path bit-for-bit
     samples2, _ = ldm.sample_log_diff_sampler(cond, n, "DDIM", int(g["steps"]), size_len=cfg["latent_w"],
                                               unconditional_guidance_scale=float(g["scale"]),
