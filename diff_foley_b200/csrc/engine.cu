@@ -77,6 +77,40 @@ __global__ void pack_head_kernel(const float* __restrict__ src, float* __restric
   dst[(co * 9 + tap) * C + c] = src[i];
 }
 
+// FeedForward.net[2] followed by SpatialTransformer.proj_out are two linear maps with nothing but the
+// residual add between them (attention_openai.py:211-215,259-261):
+//   out = Wp (Wf h + bf + x) + bp + x_in = (Wp Wf) h + Wp x + (Wp bf + bp) + x_in
+// so at finalize the two weight matrices are merged into ONE [C, 4C + C] matrix [Wp Wf | Wp] (+ bias
+// Wp bf + bp) and the plan runs a single GEMM over the concatenated operand [h | x] (second A source).
+// 32x32 output tile per CTA, fp16 inputs (the packed weights), fp32 accumulation.
+__global__ void __launch_bounds__(1024)
+fuse_ffproj_kernel(const __half* __restrict__ wp, const __half* __restrict__ wf, const float* __restrict__ bf,
+                   const float* __restrict__ bp, int C, int C4, __half* __restrict__ dst, float* __restrict__ bdst) {
+  __shared__ float sp[32][33], sf[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.y * 32 + ty, k = blockIdx.x * 32 + tx;
+  const int ldd = C4 + C;
+  float acc = 0.f;
+  for (int j0 = 0; j0 < C; j0 += 32) {
+    sp[ty][tx] = __half2float(wp[(size_t)(blockIdx.y * 32 + ty) * C + j0 + tx]);   // Wp[n, j]
+    sf[ty][tx] = (k < C4) ? __half2float(wf[(size_t)(j0 + ty) * C4 + k]) : 0.f;     // Wf[j, k]
+    __syncthreads();
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) acc += sp[ty][j] * sf[j][tx];
+    __syncthreads();
+  }
+  if (k < C4) dst[(size_t)n * ldd + k] = __float2half_rn(acc);
+  if (blockIdx.x == 0) {
+    // this column block also copies Wp into the tail columns and builds the bias (one warp per row)
+    for (int j = tx; j < C; j += 32) dst[(size_t)n * ldd + C4 + j] = wp[(size_t)n * C + j];
+    float b = 0.f;
+    for (int j = tx; j < C; j += 32) b += __half2float(wp[(size_t)n * C + j]) * bf[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+    if (tx == 0) bdst[n] = b + bp[n];
+  }
+}
+
 static inline unsigned nblk(long n) { return (unsigned)((n + 255) / 256); }
 
 // ================================================================================= structures
@@ -104,6 +138,7 @@ struct STW {
   int kv_off = 0;  // column offset of this layer's [k | v] in the fused context projection
   Norm gn, ln1, ln2, ln3;
   Lin proj_in, qkv, out1, q2, out2, geglu, ffout, proj_out;
+  Lin ffproj;  // [C, 4C + C] = [proj_out . ffout | proj_out], built at finalize
 };
 struct ConvW {
   std::string prefix;
@@ -439,6 +474,7 @@ static int register_weights(dfb_unet* e) {
     ok &= alloc_lin(e, &s.geglu, 8 * C, C, true);
     ok &= alloc_lin(e, &s.ffout, C, 4 * C, true);
     ok &= alloc_lin(e, &s.proj_out, C, C, true);
+    ok &= alloc_lin(e, &s.ffproj, C, 5 * C, true);
     if (!ok) return DFB_E_CUDA;
     if ((4 * C) % 64 != 0) {
       set_error("unsupported config: transformer width must be a multiple of 16");
@@ -519,7 +555,7 @@ struct Builder {
   int B;
   bool dry;  // first pass: only measure scratch requirements
   size_t need16 = 0, need32 = 0;
-  __half* a16[3] = {nullptr, nullptr, nullptr};
+  __half* a16[4] = {nullptr, nullptr, nullptr, nullptr};
   float* t32[3] = {nullptr, nullptr, nullptr};
   int rc = 0;
   std::shared_ptr<IGemmPlan> prev_gemm;
@@ -673,15 +709,28 @@ struct Builder {
                                 dpad, scale, st);
       });
     }
-    gemm(A2, s.out2, g, ep_f32(x0, C, x1, C));  // x2 -> x0 buffer (old x0 is dead)
+    static const bool fuse_ffproj = getenv("DFB_NO_FFPROJ") == nullptr;
+    {
+      IGemmEpilogue ep = ep_f32(x0, C, x1, C);  // x2 -> x0 buffer (old x0 is dead)
+      if (fuse_ffproj) ep.out_f16 = a16[3];      // + the fp16 copy the merged ff/proj GEMM reads
+      gemm(A2, s.out2, g, ep);
+    }
     // --- GEGLU feed-forward
     {
       const Norm n = s.ln3;
       op([=](cudaStream_t st) { return layernorm_launch(x0, M, C, n.g, n.b, 1e-5f, A0, st); });
     }
     gemm(A0, s.geglu, g, ep_f16(A1, 4 * C, ACT_GEGLU));
-    gemm(A1, s.ffout, gemm_geom(M, 4 * C), ep_f16(A2, C, ACT_NONE, x0, C));
-    gemm(A2, s.proj_out, g, ep_f32(out, C, xin, C));
+    if (fuse_ffproj) {
+      // ff.net[2] and proj_out merged (see fuse_ffproj_kernel): [h | x2] x [Wp Wf | Wp]^T + b' + x_in
+      IGemmGeom gf = gemm_geom(M, 4 * C);
+      gf.C2 = C;
+      gf.A2 = a16[3];
+      gemm(A1, s.ffproj, gf, ep_f32(out, C, xin, C));
+    } else {
+      gemm(A1, s.ffout, gemm_geom(M, 4 * C), ep_f16(A2, C, ACT_NONE, x0, C));
+      gemm(A2, s.proj_out, g, ep_f32(out, C, xin, C));
+    }
   }
 
   void downsample(const ConvW& d, const float* x, int H, int W, float* out) {
@@ -737,6 +786,7 @@ static int build_plan(dfb_unet* e, int B, Plan** out) {
     if (b.dry) {
       // the measuring pass never launches: give every buffer a distinct non-null fake address so
       // the planners' pointer validation passes
+      b.a16[3] = reinterpret_cast<__half*>((uintptr_t)0x10000 * 13);
       for (int i = 0; i < 3; ++i) {
         b.a16[i] = reinterpret_cast<__half*>((uintptr_t)0x10000 * (i + 1));
         b.t32[i] = reinterpret_cast<float*>((uintptr_t)0x10000 * (i + 4));
@@ -746,6 +796,8 @@ static int build_plan(dfb_unet* e, int B, Plan** out) {
       t16b = reinterpret_cast<__half*>((uintptr_t)0x10000 * 11);
       emb_all = reinterpret_cast<float*>((uintptr_t)0x10000 * 12);
     } else {
+      b.a16[3] = (__half*)palloc(s_need16 * sizeof(__half));
+      if (!b.a16[3]) { set_error("plan: cudaMalloc failed"); return DFB_E_CUDA; }
       for (int i = 0; i < 3; ++i) {
         b.a16[i] = (__half*)palloc(s_need16 * sizeof(__half));
         b.t32[i] = (float*)palloc(s_need32 * sizeof(float));
@@ -1050,6 +1102,13 @@ int dfb_unet_finalize(dfb_handle h) {
     set_error(s);
     return DFB_E_STATE;
   }
+  cudaSetDevice(h->device);
+  for (auto& s : h->sts) {
+    const int C = s.C, C4 = 4 * C;
+    fuse_ffproj_kernel<<<dim3((C4 + 31) / 32, C / 32), 1024>>>(s.proj_out.w, s.ffout.w, s.ffout.b, s.proj_out.b, C,
+                                                              C4, s.ffproj.w, s.ffproj.b);
+  }
+  DFB_CUDA_OK(cudaGetLastError());
   DFB_CUDA_OK(cudaDeviceSynchronize());
   h->finalized = true;
   return 0;
