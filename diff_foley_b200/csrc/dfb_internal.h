@@ -104,6 +104,8 @@ struct IGemmEpilogue {
   const float* rowvec;      // optional per-sample vector [B, ld_rowvec] added to every row of sample b
   int ld_rowvec;
   int rows_per_sample;      // rows (output positions) per sample, for rowvec
+  const int* rowvec_row;    // optional device scalar: use row *rowvec_row of `rowvec` for EVERY sample (the
+                            // sampler's table of per-step timestep embeddings, indexed by its step counter)
   const float* residual;    // optional fp32 [M, ld_res]
   const __half* residual_f16;  // optional fp16 [M, ld_res] (CAVP ResNet identity path)
   int ld_res;

@@ -220,7 +220,16 @@ struct dfb_unet {
     cudaGraphExec_t exec = nullptr;
     cudaStream_t cap_stream = nullptr;
     int cap_S = 0;
+    // table of SiLU(time_embed(t)) -> all 22 emb_layers for every step of the schedule: the timestep
+    // embedding depends on t and the weights only, so the sampler computes it once per schedule (M = S
+    // rows through the same GEMMs) instead of 4 launches inside every step; the step's convs pick row
+    // `*step` (IGemmEpilogue::rowvec_row)
+    float* emb_tab = nullptr;            // [EMB_TAB_ROWS, emb_all.N]
+    __half *emb_a = nullptr, *emb_b = nullptr;
+    std::vector<long long> tab_steps;    // schedule the table was built for
+    long long tab_epoch = -1;
   } smp;
+  long long weights_epoch = 0;  // bumped by set_weight / finalize
 
   template <typename T>
   T* dalloc(size_t n, bool zero = true) {
@@ -549,10 +558,13 @@ static int register_weights(dfb_unet* e) {
 }
 
 // ================================================================================ plan builder
+constexpr int EMB_TAB_ROWS = 256;  // longest schedule served from the embedding table
+
 struct Builder {
   dfb_unet* e;
   Plan* plan;
   int B;
+  const int* rowvec_row = nullptr;  // table mode: device step counter selecting the emb row
   bool dry;  // first pass: only measure scratch requirements
   size_t need16 = 0, need32 = 0;
   __half* a16[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -637,6 +649,7 @@ struct Builder {
       ep.rowvec = emb_all ? emb_all + r.emb_off : nullptr;
       ep.ld_rowvec = emb_ld;
       ep.rows_per_sample = HW;
+      ep.rowvec_row = rowvec_row;
       gemm(gn_out, r.conv1, conv3x3_geom(B, H, W, r.cin), ep);
     }
     {
@@ -751,8 +764,9 @@ struct Builder {
   }
 };
 
-static int build_plan(dfb_unet* e, int B, Plan** out) {
-  auto it = e->plans.find(B);
+static int build_plan(dfb_unet* e, int B, Plan** out, bool emb_table = false) {
+  const int plan_key = B + (emb_table ? (1 << 20) : 0);
+  auto it = e->plans.find(plan_key);
   if (it != e->plans.end()) {
     *out = it->second.get();
     return 0;
@@ -779,6 +793,7 @@ static int build_plan(dfb_unet* e, int B, Plan** out) {
   for (int pass = 0; pass < 2; ++pass) {
     Builder b;
     b.e = e; b.plan = plan.get(); b.B = B; b.dry = (pass == 0);
+    if (emb_table) b.rowvec_row = e->smp.step;
     std::vector<float*> skips;
     float* hbuf[3] = {nullptr, nullptr, nullptr};
     __half *t16a = nullptr, *t16b = nullptr;
@@ -810,7 +825,9 @@ static int build_plan(dfb_unet* e, int B, Plan** out) {
       if (!t16a || !t16b || !emb_all) { set_error("plan: cudaMalloc failed"); return DFB_E_CUDA; }
     }
     // ---- timestep embedding MLP + all emb_layers (util.py:151-171, openai_unetmodel.py:723-724,263)
-    {
+    if (emb_table) {
+      emb_all = e->smp.emb_tab;  // precomputed per schedule by the sampler, row = step
+    } else {
       dfb_unet* eng = e;
       const int Bc = B;
       __half* o = t16a;
@@ -940,7 +957,7 @@ static int build_plan(dfb_unet* e, int B, Plan** out) {
     }
   }
   *out = plan.get();
-  e->plans[B] = std::move(plan);
+  e->plans[plan_key] = std::move(plan);
   return 0;
 }
 
@@ -1087,6 +1104,7 @@ int dfb_unet_set_weight(dfb_handle h, const char* name, const float* src, const 
   if (r) return r;
   h->pending.erase(name);
   h->finalized = false;
+  h->weights_epoch++;
   return 0;
 }
 
@@ -1163,7 +1181,7 @@ int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* unco
     if (sm.exec) { cudaGraphExecDestroy(sm.exec); sm.exec = nullptr; }
     sm.coefs = h->dalloc<float>((size_t)S * 5);
     sm.tsteps = h->dalloc<long long>(S);
-    sm.step = h->dalloc<int>(1);
+    if (sm.step == nullptr) sm.step = h->dalloc<int>(1);  // (table-mode plans keep this pointer)
     sm.t_cur = h->dalloc<long long>(b_eff);
     sm.eps = h->dalloc<float>(2 * n_lat);
     sm.ctx_cat = h->dalloc<float>(2 * n_ctx);
@@ -1186,8 +1204,38 @@ int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* unco
   h->last_launches = 0;
   int r = compute_context(h, sm.ctx_cat, b_eff, ctx_len, s);
   if (r) return r;
+  // ---- per-schedule table of timestep embeddings (see Sampler::emb_tab)
+  static const bool no_tab = getenv("DFB_NO_EMB_TABLE") != nullptr;
+  const bool use_tab = !no_tab && S <= EMB_TAB_ROWS;
+  if (use_tab) {
+    const int mc = c.model_channels, td = h->time_dim;
+    if (sm.emb_tab == nullptr) {
+      sm.emb_tab = h->dalloc<float>((size_t)EMB_TAB_ROWS * h->emb_all.N);
+      sm.emb_a = h->dalloc<__half>((size_t)EMB_TAB_ROWS * std::max(mc, td));
+      sm.emb_b = h->dalloc<__half>((size_t)EMB_TAB_ROWS * td);
+      if (!sm.emb_tab || !sm.emb_a || !sm.emb_b) return DFB_E_CUDA;
+    }
+    if (sm.tab_epoch != h->weights_epoch || sm.tab_steps != ht) {
+      r = temb_launch(sm.tsteps, 0, S, mc, sm.emb_a, s);
+      const struct { const __half* a; const Lin* lin; int K; IGemmEpilogue ep; } chain[3] = {
+          {sm.emb_a, &h->time1, mc, Builder::ep_f16(sm.emb_b, td, ACT_SILU)},
+          {sm.emb_b, &h->time2, td, Builder::ep_f16(sm.emb_a, td, ACT_SILU)},
+          {sm.emb_a, &h->emb_all, td, Builder::ep_f32(sm.emb_tab, h->emb_all.N)}};
+      for (int i = 0; i < 3 && !r; ++i) {
+        IGemmPlan ip;
+        IGemmEpilogue ep = chain[i].ep;
+        ep.bias = chain[i].lin->b;
+        r = igemm_plan(&ip, chain[i].a, chain[i].lin->w, chain[i].lin->N, gemm_geom(S, chain[i].K), ep, 0);
+        if (!r) r = igemm_launch(ip, s);
+      }
+      if (r) return r;
+      sm.tab_steps = ht;
+      sm.tab_epoch = h->weights_epoch;
+      h->last_launches += 4;
+    }
+  }
   Plan* p = nullptr;
-  r = build_plan(h, b_eff, &p);
+  r = build_plan(h, b_eff, &p, use_tab);
   if (r) return r;
   h->cur_x = x; h->cur_x_repeat = 2; h->cur_t = sm.t_cur; h->cur_t_is_float = 0; h->cur_out = sm.eps;
   auto one_step = [&](cudaStream_t st) -> int {

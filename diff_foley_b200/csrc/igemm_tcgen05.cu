@@ -52,6 +52,7 @@ struct IGemmKParams {
   const float* rowvec;
   int ld_rowvec;
   int rows_per_sample;
+  const int* rowvec_row;
   const float* residual;
   const __half* residual_f16;
   int ld_res;
@@ -202,6 +203,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     float4 rv[UNR], res[UNR];
   };
   // every load of a batch is issued (at clamped, always-valid addresses) before any of them is consumed
+  const int rv_row = (has_rv && p.rowvec_row != nullptr) ? __ldg(p.rowvec_row) : -1;
   auto epi_fetch = [&](int base, EpiOps& o) {
     int bsm[UNR];
 #pragma unroll
@@ -209,7 +211,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       const int lr = base + u * NW * RPW;
       const int2 ri = lds_i2(tab + 8u * (uint32_t)max(min(lr, Rz - 1), 0));
       o.m[u] = (lane_on && lr < Rz) ? ri.x : -1;
-      bsm[u] = ri.y;
+      bsm[u] = rv_row >= 0 ? rv_row : ri.y;
       o.rv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       o.res[u] = o.rv[u];
     }
@@ -798,6 +800,7 @@ int igemm_launch(const IGemmPlan& plan, cudaStream_t stream) {
   kp.out_f32 = plan.e.out_f32; kp.out_f16 = plan.e.out_f16; kp.ldo = plan.e.ldo;
   kp.bias = plan.e.bias; kp.rowvec = plan.e.rowvec; kp.ld_rowvec = plan.e.ld_rowvec;
   kp.rows_per_sample = plan.e.rows_per_sample;
+  kp.rowvec_row = plan.e.rowvec_row;
   kp.residual = plan.e.residual; kp.residual_f16 = plan.e.residual_f16; kp.ld_res = plan.e.ld_res;
   kp.act = plan.e.act;
   kp.splits = plan.splits;

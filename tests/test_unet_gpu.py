@@ -116,14 +116,24 @@ def test_fused_ddim_matches_reference_sampler(name, cfg):
         err_native = rel_l2(mel_native, gv["mel"])
         print(f"[parity] {name}: DECODED MEL, native sampler + native decoder = {err_native:.3e}")
         assert err_native < 2e-3
-    # the host-loop path (apply_model + dfb_ddim_step) must agree with the fused graph path bit-for-bit
+    # the host-loop path (apply_model + dfb_ddim_step) must agree with the fused graph path
     samples2, _ = ldm.sample_log_diff_sampler(cond, n, "DDIM", int(g["steps"]), size_len=cfg["latent_w"],
                                               unconditional_guidance_scale=float(g["scale"]),
                                               unconditional_conditioning=torch.zeros_like(cond), x_T=x_T,
                                               callback=lambda i: None)
     torch.cuda.synchronize()
+    # Not bit-for-bit: the fused sampler takes the 22 emb_layers vectors from its per-schedule table, a
+    # 25-row GEMM whose K-split plan -- hence fp32 summation order -- differs from the per-step 2-row one.
+    # A 1e-7 perturbation is enough to decorrelate the fp16 operand roundings of 25 UNet passes, so the two
+    # paths end up two independent draws of the same rounding noise: each within tolerance of the
+    # reference, about sqrt(2) x that noise apart.  Each path is bit-reproducible run to run.
     print(f"[parity] {name}: fused vs host-loop rel-L2 = {rel_l2(samples2, samples):.3e}")
-    assert rel_l2(samples2, samples) < 1e-6
+    assert rel_l2(samples2, samples) < 1e-3
+    assert rel_l2(samples2, g["samples"]) < 2e-2
+    samples3, _ = ldm.sample_log_diff_sampler(cond, n, "DDIM", int(g["steps"]), size_len=cfg["latent_w"],
+                                              unconditional_guidance_scale=float(g["scale"]),
+                                              unconditional_conditioning=torch.zeros_like(cond), x_T=x_T)
+    assert torch.equal(samples3, samples), "the fused sampler must be bit-reproducible"
 
 
 def test_sharded_sampler_world1_matches_fused():
