@@ -155,7 +155,8 @@ def test_groupnorm(C0, C1, HW, eps, silu):
     assert rel_l2(raw.float(), x) < 6e-4
 
 
-@pytest.mark.parametrize("rows,C", [(2048, 320), (512, 640), (128, 1280), (32, 1280), (7, 256)])
+@pytest.mark.parametrize("rows,C", [(2048, 320), (512, 640), (128, 1280), (32, 1280), (7, 256),
+                                    (16384, 320), (4097, 640), (4096, 384), (8192, 1280)])
 def test_layernorm(rows, C):
     g = torch.Generator(device="cpu").manual_seed(rows + C)
     x = (torch.randn(rows, C, generator=g) * 1.7 + 0.3).to(DEV)
@@ -348,4 +349,19 @@ def test_softmax_rows():
     L.check(L.lib().dfb_softmax_rows(L.ptr(x), 1024, 1024, 512 ** -0.5, L.ptr(out), L.cur_stream()), "softmax")
     sync()
     ref = torch.softmax(x * 512 ** -0.5, dim=1)
+    assert rel_l2(out.float(), ref) < 1e-3
+
+
+def test_groupnorm_large_batch():
+    """B_eff = 16 at the 16x64 level: the grid already fills the machine, minimal cluster size."""
+    g = torch.Generator(device="cpu").manual_seed(77)
+    B, HW, C = 16, 1024, 320
+    x = (torch.randn(B, HW, C, generator=g) * 1.3 - 0.2).to(DEV)
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(C, generator=g)).to(DEV)
+    out = torch.empty(B, HW, C, device=DEV, dtype=torch.float16)
+    L.check(L.lib().dfb_groupnorm(L.ptr(x), C, None, 0, B, HW, L.ptr(gamma), L.ptr(beta), 1e-5, 1, L.ptr(out),
+                                  None, L.cur_stream()), "dfb_groupnorm")
+    sync()
+    ref = F.silu(F.group_norm(x.permute(0, 2, 1), 32, gamma, beta, 1e-5)).permute(0, 2, 1)
     assert rel_l2(out.float(), ref) < 1e-3
