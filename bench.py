@@ -248,7 +248,7 @@ def run_ours(args):
         ach_gbs = ig_bytes / (ig_ms / 1e3) / 1e9
         ach_tf = ig_flops / (ig_ms / 1e3) / 1e12
         hbm_bound = (ig_bytes / pk["hbm"] / 1e9) >= (ig_flops / pk["tf_sust"] / 1e12)
-        # DRAM traffic of the same 195 launches from the committed ncu pass (B_eff = 2 only); null otherwise
+        # DRAM traffic of the same igemm launches from the committed ncu pass (B_eff = 2 only); null otherwise
         traffic, traffic_src = None, None
         tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_igemm_dram_traffic.json")
         if C == 1 and os.path.exists(tpath):
@@ -265,7 +265,7 @@ def run_ours(args):
             "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk["src"],
             "launches_per_forward": len(ig), "kernel_ms_per_forward": ig_ms,
             "kernel_ms_per_forward_event_profile": ig_ms_raw, "all_kernels_ms_per_forward_event_profile": all_ms,
-            "how": "algorithmic bytes (or flops) of the 195 igemm launches of one UNet forward / (igemm share of the per-launch event profile x graph-timed UNet step)",
+            "how": f"algorithmic bytes (or flops) of the {len(ig)} igemm launches of one UNet forward / (igemm share of the per-launch event profile x graph-timed UNet step)",
             "share_of_step": ig_ms / all_ms if all_ms else None,
             "algorithmic_bytes_per_forward": ig_bytes, "weight_bytes_per_forward": w_bytes,
             "algorithmic_flops_per_forward": ig_flops,
