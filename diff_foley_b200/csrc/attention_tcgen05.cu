@@ -48,6 +48,7 @@ struct AttParams {
   __half* out;
   int ldo;
   int heads, Lq, Lk, d, dpad, KB, nblocks, tmem_cols;
+  int kvs;  // depth of the K/V tile ring (2..4)
   float scale_log2;  // d^-0.5 * log2(e)
   unsigned long long* trace;  // optional timeline record (diagnostics)
 };
@@ -64,20 +65,24 @@ __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// smem carve-up (bytes), all tiles in the [chunk][row][8 halves] layout
+// smem carve-up (bytes), all tiles in the [chunk][row][8 halves] layout.  K/V tiles live in a ring of `kvs`
+// stages (K then V per stage): with only two, a stage is refilled after the P V of its previous block,
+// and the ~1 us L2 round trip of that load -- not the softmax -- set the pace of the key loop (ncu source
+// view: 31 % of all warp samples on the softmax warps' wait for S).
 struct AttSmem {
   int q_bytes, kv_tile_bytes, p_bytes;
-  int off_q, off_k[2], off_v[2], off_p[2], off_bar, off_xch, total;
+  int off_q, off_kv, off_p, off_bar, off_xch, total;
 };
-__host__ __device__ inline AttSmem att_smem_layout(int dpad, int KB) {
+constexpr int ATT_MAX_KVS = 4;
+__host__ __device__ inline AttSmem att_smem_layout(int dpad, int KB, int kvs) {
   AttSmem s;
   s.q_bytes = ATT_BM * dpad * 2;
   s.kv_tile_bytes = KB * dpad * 2;
   s.p_bytes = ATT_BM * KB * 2;
   int o = 0;
   s.off_q = o; o += s.q_bytes;
-  for (int i = 0; i < 2; ++i) { s.off_k[i] = o; o += s.kv_tile_bytes; s.off_v[i] = o; o += s.kv_tile_bytes; }
-  for (int i = 0; i < 2; ++i) { s.off_p[i] = o; o += s.p_bytes; }
+  s.off_kv = o; o += kvs * 2 * s.kv_tile_bytes;
+  s.off_p = o; o += 2 * s.p_bytes;
   s.off_bar = (o + 15) & ~15;
   s.off_xch = s.off_bar + 16 * 8 + 16;            // float [2 parities][2 halves][128 rows] maxima + [2][128] sums
   s.total = s.off_xch + (4 + 2) * ATT_BM * 4;
@@ -95,15 +100,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   extern __shared__ uint8_t att_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_raw) + 127) &
                                              ~static_cast<uintptr_t>(127));
-  const AttSmem L = att_smem_layout(p.dpad, p.KB);
+  const AttSmem L = att_smem_layout(p.dpad, p.KB, p.kvs);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;    // [2]
-  uint64_t* kv_empty = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;     // [2]
-  uint64_t* p_full = bars + 7;     // [2], 128 arrivals each
-  uint64_t* pv_done = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* s_full = bars + 1;     // [2]
+  uint64_t* p_full = bars + 3;     // [2], 256 arrivals each
+  uint64_t* pv_done = bars + 5;
+  uint64_t* kv_full = bars + 6;                 // [kvs]
+  uint64_t* kv_empty = bars + 6 + ATT_MAX_KVS;  // [kvs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * ATT_MAX_KVS);
+  const int KVS = p.kvs;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) trace_mark(p.trace, 0);
@@ -119,9 +125,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   if (warp == 1) {
     if (lane == 0) {
       mbar_init(q_full, 1);
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < KVS; ++i) {
         mbar_init(&kv_full[i], 1);
         mbar_init(&kv_empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
         mbar_init(&s_full[i], 1);
         mbar_init(&p_full[i], 256);
       }
@@ -139,7 +147,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   if (threadIdx.x == 0) trace_mark(p.trace, 1);
   pdl_launch_dependents();  // only after our own wait: at most two grids of the chain overlap
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_s[2] = {tmem_base, tmem_base + NQ * 16};  // S double buffer: 2 x (NQ*16 fp32 columns)
+  // S double buffer: 2 x (NQ*16 fp32 columns) at tmem_base + s*NQ*16 (arithmetic, not a runtime-indexed
+  // array: that would live in local memory)
   const uint32_t tm_o = tmem_base + 2 * NQ * 16;               // O: dpad fp32 columns
 
   if (warp == 0) {
@@ -151,12 +160,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       for (int c = 0; c < nch; ++c)
         tma_load_2d(smem + L.off_q + c * (ATT_BM * 16), &tmQ, q_full, col0 + 8 * c, b * p.Lq + q0);
       for (int j = 0; j < nb; ++j) {
-        const int s = j & 1;
-        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[s], 2 * L.kv_tile_bytes);
+        const int st = j % KVS;
+        mbar_wait(&kv_empty[st], ((j / KVS) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[st], 2 * L.kv_tile_bytes);
+        uint8_t* kt = smem + L.off_kv + st * 2 * L.kv_tile_bytes;
         for (int c = 0; c < nch; ++c) {
-          tma_load_2d(smem + L.off_k[s] + c * (KB * 16), &tmK, &kv_full[s], col0 + 8 * c, b * p.Lk + j * KB);
-          tma_load_2d(smem + L.off_v[s] + c * (KB * 16), &tmV, &kv_full[s], col0 + 8 * c, b * p.Lk + j * KB);
+          tma_load_2d(kt + c * (KB * 16), &tmK, &kv_full[st], col0 + 8 * c, b * p.Lk + j * KB);
+          tma_load_2d(kt + L.kv_tile_bytes + c * (KB * 16), &tmV, &kv_full[st], col0 + 8 * c, b * p.Lk + j * KB);
         }
       }
     }
@@ -171,10 +181,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     const uint32_t sq = smem_u32(smem + L.off_q);
     auto issue_s = [&](int j) {
       const int s = j & 1;
-      const uint32_t sk = smem_u32(smem + L.off_k[s]);
+      const uint32_t sk = smem_u32(smem + L.off_kv + (j % KVS) * 2 * L.kv_tile_bytes);
 #pragma unroll 1
       for (int k = 0; k < p.dpad / 16; ++k)
-        umma_f16_ss(tm_s[s], desc(sq + k * 2 * q_lbo, q_lbo, 128), desc(sk + k * 2 * k_lbo, k_lbo, 128),
+        umma_f16_ss(tmem_base + (uint32_t)(s * NQ * 16), desc(sq + k * 2 * q_lbo, q_lbo, 128), desc(sk + k * 2 * k_lbo, k_lbo, 128),
                     idesc_s, k > 0 ? 1u : 0u);
       umma_commit(&s_full[s]);
     };
@@ -187,7 +197,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       const int s = j & 1;
       if (j + 1 < nb) {
         const int s1 = (j + 1) & 1;
-        mbar_wait(&kv_full[s1], ((j + 1) >> 1) & 1);
+        mbar_wait(&kv_full[(j + 1) % KVS], ((j + 1) / KVS) & 1);
         // S buffer s1 was last read by the softmax of block j-1 (done once P_{j-1} is full)
         if (j >= 1) mbar_wait(&p_full[s1], ((j - 1) >> 1) & 1);
         tc_fence_after();
@@ -197,15 +207,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       mbar_wait(&p_full[s], (j >> 1) & 1);
       tc_fence_after();
       if (lane == 0) {
-        const uint32_t sp = smem_u32(smem + L.off_p[s]);
-        const uint32_t sv = smem_u32(smem + L.off_v[s]);
+        const uint32_t sp = smem_u32(smem + L.off_p + s * L.p_bytes);
+        const uint32_t sv = smem_u32(smem + L.off_kv + (j % KVS) * 2 * L.kv_tile_bytes + L.kv_tile_bytes);
 #pragma unroll 1
         for (int k = 0; k < KB / 16; ++k)
           umma_f16_ss(tm_o, desc(sp + k * 2 * q_lbo, q_lbo, 128),
                       // V: MN-major; 8-key groups are 128 B apart (LBO), 8-column groups KB*16 B (SBO)
                       desc(sv + k * 256, 128, k_lbo), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(pv_done);
-        umma_commit(&kv_empty[s]);
+        umma_commit(&kv_empty[j % KVS]);
       }
       __syncwarp();
     }
@@ -219,58 +229,77 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     float* xsum = xmax + 4 * ATT_BM;                             // [half][row]
     constexpr int NQH = NQ / 2;         // chunks per thread per block
     float m_run = -INFINITY, l_run = 0.f;  // l_run: this thread's share of the row sum
+    const float sl = p.scale_log2;
+    const uint32_t p_base = smem_u32(smem + L.off_p) + (uint32_t)r * 16u;
     for (int j = 0; j < nb; ++j) {
       const int s = j & 1;
       mbar_wait(&s_full[s], (j >> 1) & 1);
       tc_fence_after();
       const int kvalid = min(KB, p.Lk - j * KB);  // keys of this block that exist
-      uint8_t* prow = smem + L.off_p[s] + r * 16;
+      const bool full = (kvalid == KB);           // CTA-uniform: only a ragged last block is masked
+      const uint32_t prow = p_base + (uint32_t)s * (uint32_t)L.p_bytes;
+      const uint32_t ts = tmem_base + (uint32_t)(s * NQ * 16) + lane_off;
       // ---- one TMEM pass: this thread's chunks of the S row into registers
       uint32_t raw[NQH][16];
 #pragma unroll
       for (int q = 0; q < NQH; ++q)
-        if ((2 * q + half) * 16 < KB) tmem_ld_32x16(tm_s[s] + lane_off + (2 * q + half) * 16, raw[q]);
+        if ((2 * q + half) * 16 < KB) tmem_ld_32x16(ts + (2 * q + half) * 16, raw[q]);
       tmem_ld_wait();
-      float mx = -INFINITY;
+      // the softmax warps are bound by their own instruction stream: the common (full-block) path is
+      // FMNMX / FFMA / MUFU.EX2 / FADD / half a F2FP per score, nothing else; four independent chains
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (full) {
 #pragma unroll
-      for (int q = 0; q < NQH; ++q)
-        if ((2 * q + half) * 16 < KB) {
+        for (int q = 0; q < NQH; ++q)
+          if ((2 * q + half) * 16 < KB) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if ((2 * q + half) * 16 + i < kvalid) mx = fmaxf(mx, __uint_as_float(raw[q][i]));
-        }
+            for (int i = 0; i < 16; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(raw[q][i]));
+          }
+      } else {
+#pragma unroll
+        for (int q = 0; q < NQH; ++q)
+          if ((2 * q + half) * 16 < KB) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if ((2 * q + half) * 16 + i < kvalid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(raw[q][i]));
+          }
+      }
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       // ---- row maximum across the two threads of this row
       xmax[(s * 2 + half) * ATT_BM + r] = mx;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + sub) : "memory");
       mx = fmaxf(mx, xmax[(s * 2 + (half ^ 1)) * ATT_BM + r]);
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float alpha = exp2f(m_run - m_new);  // 0 on the first block (m_run = -inf)
+      const float m_new = fmaxf(m_run, mx * sl);
+      const float alpha = ex2_approx(m_run - m_new);  // 0 on the first block (m_run = -inf)
+      const float neg_m = -m_new;
       // ---- p = exp2(s*scale - m), partial row sum, fp16 P tile in the canonical K-major layout
-      float psum = 0.f;
+      float ps4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int q = 0; q < NQH; ++q)
         if ((2 * q + half) * 16 < KB) {
           const int c0 = (2 * q + half) * 16;
           float e[16];
+          if (full) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float v = exp2f(fmaf(__uint_as_float(raw[q][i]), p.scale_log2, -m_new));
-            e[i] = (c0 + i < kvalid) ? v : 0.f;
-            psum += e[i];
+            for (int i = 0; i < 16; ++i) {
+              e[i] = ex2_approx(fmaf(__uint_as_float(raw[q][i]), sl, neg_m));
+              ps4[i & 3] += e[i];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float v = ex2_approx(fmaf(__uint_as_float(raw[q][i]), sl, neg_m));
+              e[i] = (c0 + i < kvalid) ? v : 0.f;
+              ps4[i & 3] += e[i];
+            }
           }
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            __half2 h0 = __floats2half2_rn(e[8 * g + 0], e[8 * g + 1]);
-            __half2 h1 = __floats2half2_rn(e[8 * g + 2], e[8 * g + 3]);
-            __half2 h2 = __floats2half2_rn(e[8 * g + 4], e[8 * g + 5]);
-            __half2 h3 = __floats2half2_rn(e[8 * g + 6], e[8 * g + 7]);
-            uint4 u;
-            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(prow + ((c0 >> 3) + g) * (ATT_BM * 16)) = u;
-          }
+          for (int g = 0; g < 2; ++g)
+            sts_u4(prow + (uint32_t)(((c0 >> 3) + g) * (ATT_BM * 16)), pack_h2(e[8 * g + 0], e[8 * g + 1]),
+                   pack_h2(e[8 * g + 2], e[8 * g + 3]), pack_h2(e[8 * g + 4], e[8 * g + 5]),
+                   pack_h2(e[8 * g + 6], e[8 * g + 7]));
         }
-      l_run = l_run * alpha + psum;
+      l_run = fmaf(l_run, alpha, (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]));
       m_run = m_new;
       fence_proxy_async_smem();  // generic-proxy P stores -> visible to the tensor core (async proxy)
       // ---- correction: O *= alpha, in TMEM, once the previous P V has landed (columns split by half)
@@ -392,7 +421,15 @@ int attention_launch(const __half* q, int ldq, const __half* k, int ldk, const _
   if (!rc) rc = get_tmap(&tk, k, ldk, (long)B * Lk, dpad, p.KB);
   if (!rc) rc = get_tmap(&tv, v, ldv, (long)B * Lk, dpad, p.KB);
   if (rc) return rc;
-  const AttSmem L = att_smem_layout(dpad, p.KB);
+  // K/V ring depth: as deep as the key loop needs (<= 4) while two CTAs still share an SM when the head
+  // dim allows it (~110 KB per CTA), else whatever fits in one SM's shared memory
+  p.kvs = 2;
+  for (int k = 3; k <= ATT_MAX_KVS && k <= std::max(2, p.nblocks); ++k) {
+    const int tot = att_smem_layout(dpad, p.KB, k).total + 128;
+    const bool two_ctas = (nq == 4) && att_smem_layout(dpad, p.KB, 2).total + 128 <= 110 * 1024;
+    if (tot <= (two_ctas ? 110 : 200) * 1024) p.kvs = k;
+  }
+  const AttSmem L = att_smem_layout(dpad, p.KB, p.kvs);
   dim3 grid((Lq + ATT_BM - 1) / ATT_BM, B * heads);
   note("attention", 4.0 * B * heads * (double)Lq * Lk * d,
        2.0 * B * heads * ((double)Lq * d * 2 + (double)Lk * d * 2), Lq, Lk, d, 1, grid.x * grid.y);

@@ -148,6 +148,123 @@ groupnorm_kernel(const float* __restrict__ src0, int C0, const float* __restrict
 }
 
 
+// ---- v2 (default): pixel-major CTAs.  The kernel above gives every (sample, group) its own cluster, so
+// a thread's loads are 8 bytes out of a 40-160 byte run per pixel and the per-element index math (runtime
+// div / mod) dominates the instruction stream.  Here a CTA owns CW consecutive channels (a whole number of
+// groups, >= 128 bytes per pixel) x a contiguous run of pixels; thread (ty, tx) keeps channel pair tx of
+// pixels ty, ty + NY, ... in registers, so a warp's loads are contiguous runs, the channel -- hence the
+// group, gamma, beta, source tensor -- of a thread never changes, and there is no division in any loop.
+// grid = (P pixel chunks, C / CW channel chunks, B), cluster (P,1,1).  Statistics: per-thread partials about
+// the group's pivot -> shared memory, one warp per group sums them in a fixed order -> st.async push of
+// the group's (s1, s2) to every CTA of the cluster (as in v1) -> every thread sums the P slots of its own
+// group in rank order.  Deterministic (no atomics).
+constexpr int GN2_THREADS = 512;
+template <int KMAX>
+__global__ void __launch_bounds__(GN2_THREADS)
+groupnorm2_kernel(const float* __restrict__ src0, int C0, const float* __restrict__ src1, int C1, int HW,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                  __half* __restrict__ out, __half* __restrict__ raw_out, int CW, int NY, int px_per,
+                  unsigned long long* trace) {
+  __shared__ float part1[GN2_THREADS], part2[GN2_THREADS];
+  __shared__ __align__(8) float2 inbox[8 * 8];   // [rank][local group] (s1, s2), pushed by the owners
+  __shared__ __align__(8) uint64_t inbox_bar;
+  if (threadIdx.x == 0) trace_mark(trace, 0);
+  const int P = gridDim.x, rank = blockIdx.x;
+  const int C = C0 + C1, cpg = C >> 5, hp = cpg >> 1;
+  const int TX = CW >> 1, ngl = CW / cpg;
+  if (P > 1) {
+    if (threadIdx.x == 0) {
+      mbar_init(&inbox_bar, 1);
+      fence_mbar_init();
+      mbar_expect_tx(&inbox_bar, (uint32_t)(P * ngl) * 8u);
+    }
+    cluster_arrive_relaxed();
+  }
+  const int b = blockIdx.z;
+  const int tid = threadIdx.x;
+  const int ty = tid / TX, tx = tid - ty * TX;
+  const bool act = ty < NY;
+  const int c = blockIdx.y * CW + 2 * tx;       // this thread's channel pair (never straddles a group)
+  const int gl = (2 * tx) / cpg;                  // local group
+  const int cg0 = blockIdx.y * CW + gl * cpg;     // first channel of the group: the pivot's channel
+  const float2 gm = __ldg(reinterpret_cast<const float2*>(gamma + c));
+  const float2 bt = __ldg(reinterpret_cast<const float2*>(beta + c));
+  const int px0 = rank * px_per;
+  const int px1 = min(px0 + px_per, HW);
+  pdl_wait();
+  if (threadIdx.x == 0) trace_mark(trace, 1);
+  pdl_launch_dependents();
+  const float* base;
+  int pstride;
+  if (c < C0) { base = src0 + (size_t)b * HW * C0 + c; pstride = C0; }
+  else { base = src1 + (size_t)b * HW * C1 + (c - C0); pstride = C1; }
+  const float piv = (cg0 < C0) ? __ldg(src0 + (size_t)b * HW * C0 + cg0)
+                               : __ldg(src1 + (size_t)b * HW * C1 + (cg0 - C0));
+  float2 v[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int px = px0 + ty + k * NY;
+    v[k] = make_float2(piv, piv);   // contributes 0 to both sums
+    if (act && px < px1) v[k] = *reinterpret_cast<const float2*>(base + (size_t)px * pstride);
+  }
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const float dx = v[k].x - piv, dy = v[k].y - piv;
+    s1 += dx + dy;
+    s2 = fmaf(dx, dx, fmaf(dy, dy, s2));
+  }
+  // group-contiguous slot: [local group][ty][pair within group]
+  const int E = hp * NY;                        // partials per group
+  if (act) {
+    const int slot = gl * E + ty * hp + (tx - gl * hp);
+    part1[slot] = s1;
+    part2[slot] = s2;
+  }
+  __syncthreads();
+  if (P > 1) cluster_wait();   // every peer's inbox barrier exists (arrive was issued at kernel entry)
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int g = warp; g < ngl; g += GN2_THREADS / 32) {
+    float a1 = 0.f, a2 = 0.f;
+    for (int e = lane; e < E; e += 32) { a1 += part1[g * E + e]; a2 += part2[g * E + e]; }
+    a1 = warp_sum(a1);
+    a2 = warp_sum(a2);
+    if (P == 1) {
+      if (lane == 0) inbox[g] = make_float2(a1, a2);
+    } else {
+      if (lane < P)
+        st_async_f2(mapa_shared(smem_u32(&inbox[rank * 8 + g]), lane), a1, a2,
+                    mapa_shared(smem_u32(&inbox_bar), lane));
+    }
+  }
+  if (P > 1) {
+    mbar_wait_cluster(&inbox_bar, 0);
+  } else {
+    __syncthreads();
+  }
+  float t1 = 0.f, t2 = 0.f;
+  for (int r = 0; r < P; ++r) { const float2 q = inbox[r * 8 + gl]; t1 += q.x; t2 += q.y; }  // rank order
+  const float inv_n = 1.f / (float)(HW * cpg);
+  const float dm = t1 * inv_n;
+  const float mean = piv + dm;
+  const float rstd = rsqrtf(fmaxf(t2 * inv_n - dm * dm, 0.f) + eps);
+  const float a0 = rstd * gm.x, a1 = rstd * gm.y;
+  const float b0 = fmaf(-mean, a0, bt.x), b1 = fmaf(-mean, a1, bt.y);
+  __half* obase = out + (size_t)b * HW * C + c;
+  __half* rbase = raw_out ? raw_out + (size_t)b * HW * C + c : nullptr;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int px = px0 + ty + k * NY;
+    if (act && px < px1) {
+      float y0 = fmaf(v[k].x, a0, b0), y1 = fmaf(v[k].y, a1, b1);
+      if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+      *reinterpret_cast<__half2*>(obase + (size_t)px * C) = __floats2half2_rn(y0, y1);
+      if (rbase) *reinterpret_cast<__half2*>(rbase + (size_t)px * C) = __floats2half2_rn(v[k].x, v[k].y);
+    }
+  }
+  if (threadIdx.x == 0) trace_mark(trace, 7);
+}
+
 // ---- slabs too large for one cluster's registers (the first-stage decoder: 128..512 channels at up to
 // 128x512 pixels, model.py:557-663 of the reference's stage1_autoencoder).  Two kernels over pixel
 // chunks: (1) every CTA reduces its chunk about the slab's pivot and writes (s1, s2) to a slot of a small
@@ -264,6 +381,47 @@ int groupnorm_launch(const float* src0, int C0, const float* src1, int C1, int B
   if (C % 64 != 0 || (C0 & 1)) {
     set_error("groupnorm: channels must be a multiple of 64 (32 groups of an even width)");
     return -1;
+  }
+  static const int gn_ver = getenv("DFB_GN") ? atoi(getenv("DFB_GN")) : 2;
+  if (gn_ver == 2) {
+    // channels per CTA: a whole number of groups, >= 32 channels (128-byte runs per pixel)
+    const int cpg = C / 32;
+    int CW = cpg * ((32 + cpg - 1) / cpg);
+    while (C % CW) CW += cpg;
+    const int TX = CW / 2;
+    const int chunks = C / CW;
+    // pixel chunks (= cluster size): aim at >= ~128 CTAs, at least 16 pixels per CTA, registers <= 16 pairs
+    int P = 1;
+    while (P < 8 && (long)chunks * B * P < 128 && HW / (P * 2) >= 16) P *= 2;
+    int NYmax = GN2_THREADS / TX;
+    while (P < 8 && (HW + P - 1) / P > NYmax * 16) P *= 2;
+    const int px_per = (HW + P - 1) / P;
+    if (px_per <= NYmax * 16 && CW / cpg <= 8) {
+      const int NY = std::min(NYmax, px_per);
+      const int kmax = (px_per + NY - 1) / NY;
+      note("groupnorm", 0.0, (double)B * HW * C * (4.0 + 2.0 + (raw_out ? 2.0 : 0.0)), B * HW, C, 0, 1, chunks * B * P);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(P, chunks, B);
+      cfg.blockDim = dim3(GN2_THREADS);
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[2];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+      attr[1].id = cudaLaunchAttributeClusterDimension;
+      attr[1].val.clusterDim.x = P;
+      attr[1].val.clusterDim.y = 1;
+      attr[1].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 2;
+      auto go = [&](auto kern) {
+        return cudaLaunchKernelEx(&cfg, kern, src0, C0, src1, C1, HW, gamma, beta, eps, silu, out, raw_out, CW, NY,
+                                  px_per, trace_record());
+      };
+      if (kmax <= 4) DFB_CUDA_OK(go(groupnorm2_kernel<4>));
+      else if (kmax <= 8) DFB_CUDA_OK(go(groupnorm2_kernel<8>));
+      else DFB_CUDA_OK(go(groupnorm2_kernel<16>));
+      return 0;
+    }
   }
   const long pairs = (long)HW * (C / 64);
   const long cap = (long)GN_THREADS * GN_MAXP;
@@ -531,6 +689,9 @@ int norm_init() {
                                    cudaSharedmemCarveoutMaxShared));
   DFB_CUDA_OK(cudaFuncSetAttribute(layernorm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                    cudaSharedmemCarveoutMaxShared));
+  DFB_CUDA_OK(cudaFuncSetAttribute(groupnorm2_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  DFB_CUDA_OK(cudaFuncSetAttribute(groupnorm2_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  DFB_CUDA_OK(cudaFuncSetAttribute(groupnorm2_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   return 0;
 }
 
