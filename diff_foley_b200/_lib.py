@@ -62,6 +62,8 @@ SIGNATURES = {
     "dfb_unet_last_launch_count": (C.c_longlong, [_vp]),
     "dfb_unet_destroy": (_i, [_vp]),
     "dfb_gemm": (_i, [_vp, _vp, _i, _i, _i, _fp, _fp, _i, _fp, _vp, _i, _vp]),
+    "dfb_gemm_stats": (_i, [_vp, _vp, _i, _i, _i, _fp, _fp, _fp, _vp, _i, _vp, C.POINTER(_i), _vp]),
+    "dfb_gemm_ln": (_i, [_vp, _vp, _i, _i, _i, _fp, _fp, _vp, _i, _f, _i, _fp, _vp, _i, _vp]),
     "dfb_conv3x3": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _i, _fp, _vp, _i, _vp]),
     "dfb_conv3x3_cat": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _vp, _i, _vp]),
     "dfb_conv_taps": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _fp, _vp, _i, _fp, _vp, _i, _vp]),

@@ -60,6 +60,46 @@ int dfb_gemm(const void* a, const void* w, int M, int N, int K, const float* bia
   return run_igemm((const __half*)a, (const __half*)w, N, gemm_geom(M, K), ep, splits, (cudaStream_t)stream);
 }
 
+int dfb_gemm_stats(const void* a, const void* w, int M, int N, int K, const float* bias, const float* residual,
+                   float* out_f32, void* out_f16, int splits, void* stats, int* tiles_n_out, void* stream) {
+  if (!a || !w || !stats || !tiles_n_out || M < 1 || N < 1 || K < 1) { set_error("dfb_gemm_stats: bad argument"); return DFB_E_INVALID; }
+  IGemmEpilogue ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.out_f32 = out_f32;
+  ep.out_f16 = (__half*)out_f16;
+  ep.ldo = N;
+  ep.bias = bias;
+  ep.residual = residual;
+  ep.ld_res = N;
+  ep.stats_out = (float2*)stats;
+  int r = kernels_init();
+  if (r) return r;
+  IGemmPlan plan;
+  r = igemm_plan(&plan, (const __half*)a, (const __half*)w, N, gemm_geom(M, K), ep, splits);
+  if (r) return r;
+  *tiles_n_out = plan.tiles_n;
+  return igemm_launch(plan, (cudaStream_t)stream);
+}
+
+int dfb_gemm_ln(const void* a, const void* w, int M, int N, int K, const float* t, const float* ln_s,
+                const void* ln_stats, int ln_tiles, float ln_eps, int act, float* out_f32, void* out_f16,
+                int splits, void* stream) {
+  if (!a || !w || !t || !ln_s || !ln_stats || M < 1 || N < 1 || K < 1 || ln_tiles < 1) { set_error("dfb_gemm_ln: bad argument"); return DFB_E_INVALID; }
+  IGemmEpilogue ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.out_f32 = out_f32;
+  ep.out_f16 = (__half*)out_f16;
+  ep.ldo = (act == ACT_GEGLU) ? N / 2 : N;
+  ep.bias = t;
+  ep.act = act;
+  ep.ln_stats = (const float2*)ln_stats;
+  ep.ln_tiles = ln_tiles;
+  ep.ln_inv_c = 1.0f / (float)K;
+  ep.ln_eps = ln_eps;
+  ep.ln_s = ln_s;
+  return run_igemm((const __half*)a, (const __half*)w, N, gemm_geom(M, K), ep, splits, (cudaStream_t)stream);
+}
+
 int dfb_conv3x3(const void* a, const void* w, int B, int H, int W, int C, int N, const float* bias,
                 const float* rowvec, const float* residual, int act, float* out_f32, void* out_f16,
                 int splits, void* stream) {

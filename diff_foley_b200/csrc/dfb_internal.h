@@ -110,6 +110,15 @@ struct IGemmEpilogue {
   const __half* residual_f16;  // optional fp16 [M, ld_res] (CAVP ResNet identity path)
   int ld_res;
   int act;                  // ACT_*
+  // LayerNorm folded into the GEMM (attention_openai.py:211-215: x + f(norm(x)) sub-blocks).  Consumer:
+  // A = raw fp16 x, weights pre-multiplied by gamma, `bias` = t_n = sum_k beta_k W[n,k] (+ the layer's
+  // bias), ln_s[n] = sum_k W'[n,k]; out = rstd_m * acc - rstd_m * mu_m * ln_s[n] + t_n with the row
+  // statistics merged from the producer's per-(row, N-tile) partials.  Producer: stats_out [M, tiles_n].
+  const float2* ln_stats;
+  int ln_tiles;
+  float ln_inv_c, ln_eps;
+  const float* ln_s;
+  float2* stats_out;
 };
 
 struct IGemmPlan {

@@ -44,6 +44,47 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, __half* __restri
   const long r = base + (n / gsz) * gstride + (n % gsz) + goff;
   dst[r * ldd + k] = __float2half_rn(src[i]);
 }
+// same row mapping, fp32 destination: staging copy of the weights that get a LayerNorm folded in at finalize
+__global__ void pack_rows_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, long N, int K,
+                                     int gsz, int gstride, int goff, long base, int ldd) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K) return;
+  const long n = i / K;
+  const int k = (int)(i - n * K);
+  const long r = base + (n / gsz) * gstride + (n % gsz) + goff;
+  dst[r * ldd + k] = src[i];
+}
+// LayerNorm folded into the Linear that consumes it (attention_openai.py:211-215: attn1(norm1(x)),
+// attn2(norm2(x)), ff(norm3(x))):  LN(x) W^T + b = rstd (x (gamma . W)^T) - rstd mu s + t  with
+//   W'[n,k] = fp16(gamma_k W[n,k]),  s_n = sum_k W'[n,k] (of the ROUNDED values: the correction must cancel
+//   what the tensor core really accumulates),  t_n = sum_k beta_k W[n,k] + b_n.
+// One CTA per output row; fold == 0 just casts (the un-fused path, DFB_NO_LNFOLD=1).
+__global__ void __launch_bounds__(128)
+ln_fold_kernel(const float* __restrict__ stage, const float* __restrict__ gamma, const float* __restrict__ beta,
+               const float* __restrict__ bias, int K, int fold, __half* __restrict__ w, float* __restrict__ s_out,
+               float* __restrict__ t_out) {
+  __shared__ float rs[4], rt[4];
+  const long n = blockIdx.x;
+  float s = 0.f, t = 0.f;
+  for (int k = threadIdx.x; k < K; k += 128) {
+    const float v = stage[n * K + k];
+    const __half h = __float2half_rn(fold ? gamma[k] * v : v);
+    w[n * K + k] = h;
+    s += __half2float(h);
+    t += (fold ? beta[k] : 0.f) * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = s; rt[threadIdx.x >> 5] = t; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_out[n] = (rs[0] + rs[1]) + (rs[2] + rs[3]);
+    t_out[n] = (rt[0] + rt[1]) + (rt[2] + rt[3]) + (bias ? bias[n] : 0.f);
+  }
+}
 __global__ void pack_vec_kernel(const float* __restrict__ src, float* __restrict__ dst, long N, int gsz,
                                 int gstride, int goff, long base) {
   const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -118,6 +159,11 @@ struct Lin {
   __half* w = nullptr;
   float* b = nullptr;
   int N = 0, K = 0;
+  // Linears that consume a LayerNorm: fp32 staging copy of the (row-permuted) weights, filled by
+  // set_weight; finalize derives w (gamma folded in), s (column sums of w) and t (beta W^T + b) from it
+  float* stage = nullptr;
+  float* s = nullptr;
+  float* t = nullptr;
 };
 struct Norm {
   float* g = nullptr;
@@ -168,6 +214,7 @@ struct dfb_unet {
   dfb_unet_cfg cfg;
   int device = 0;
   bool finalized = false;
+  bool ln_fold = true;   // LayerNorm folded into the consuming GEMMs (set at finalize; DFB_NO_LNFOLD=1 disables)
   int time_dim = 0;
   int H0 = 0, W0 = 0;
 
@@ -278,6 +325,21 @@ static void reg_linear(dfb_unet* e, const std::string& name, Lin* lin, int N, in
     pack_rows_kernel<<<nblk((long)N * K), 256>>>(src, lin->w, N, K, g, gs, goff, row_base, lin->K);
     return cudaGetLastError() == cudaSuccess ? 0 : DFB_E_CUDA;
   });
+}
+static void reg_linear_staged(dfb_unet* e, const std::string& name, Lin* lin, int N, int K, long row_base = 0,
+                              int gsz = 0, int gstride = 0, int goff = 0) {
+  reg(e, name, [=](const float* src, const int64_t* s, int nd) -> int {
+    if (!shape_is(s, nd, {N, K})) return bad_shape(name);
+    const int g = gsz ? gsz : N, gs = gsz ? gstride : N;
+    pack_rows_f32_kernel<<<nblk((long)N * K), 256>>>(src, lin->stage, N, K, g, gs, goff, row_base, lin->K);
+    return cudaGetLastError() == cudaSuccess ? 0 : DFB_E_CUDA;
+  });
+}
+static bool alloc_stage(dfb_unet* e, Lin* lin) {
+  lin->stage = e->dalloc<float>((size_t)lin->N * lin->K);
+  lin->s = e->dalloc<float>(lin->N);
+  lin->t = e->dalloc<float>(lin->N);
+  return lin->stage && lin->s && lin->t;
 }
 static void reg_vec(dfb_unet* e, const std::string& name, float** dst, int N, long base = 0, int gsz = 0,
                     int gstride = 0, int goff = 0) {
@@ -484,6 +546,7 @@ static int register_weights(dfb_unet* e) {
     ok &= alloc_lin(e, &s.ffout, C, 4 * C, true);
     ok &= alloc_lin(e, &s.proj_out, C, C, true);
     ok &= alloc_lin(e, &s.ffproj, C, 5 * C, true);
+    ok = ok && alloc_stage(e, &s.qkv) && alloc_stage(e, &s.q2) && alloc_stage(e, &s.geglu);
     if (!ok) return DFB_E_CUDA;
     if ((4 * C) % 64 != 0) {
       set_error("unsupported config: transformer width must be a multiple of 16");
@@ -498,13 +561,13 @@ static int register_weights(dfb_unet* e) {
     reg_norm(e, tb + ".norm2", &s.ln2);
     reg_norm(e, tb + ".norm3", &s.ln3);
     // self-attention: q | k | v stacked, each head padded from d to dpad rows (zero rows)
-    reg_linear(e, tb + ".attn1.to_q.weight", &s.qkv, C, C, 0, s.d, s.dpad, 0);
-    reg_linear(e, tb + ".attn1.to_k.weight", &s.qkv, C, C, hp, s.d, s.dpad, 0);
-    reg_linear(e, tb + ".attn1.to_v.weight", &s.qkv, C, C, 2 * hp, s.d, s.dpad, 0);
+    reg_linear_staged(e, tb + ".attn1.to_q.weight", &s.qkv, C, C, 0, s.d, s.dpad, 0);
+    reg_linear_staged(e, tb + ".attn1.to_k.weight", &s.qkv, C, C, hp, s.d, s.dpad, 0);
+    reg_linear_staged(e, tb + ".attn1.to_v.weight", &s.qkv, C, C, 2 * hp, s.d, s.dpad, 0);
     reg_linear(e, tb + ".attn1.to_out.0.weight", &s.out1, C, C);
     reg_vec(e, tb + ".attn1.to_out.0.bias", &s.out1.b, C);
     // cross-attention: q from x, k | v from the context (fused across all layers)
-    reg_linear(e, tb + ".attn2.to_q.weight", &s.q2, C, C, 0, s.d, s.dpad, 0);
+    reg_linear_staged(e, tb + ".attn2.to_q.weight", &s.q2, C, C, 0, s.d, s.dpad, 0);
     reg_linear(e, tb + ".attn2.to_k.weight", &e->kv_all, C, c.context_dim, s.kv_off, s.d, s.dpad, 0);
     reg_linear(e, tb + ".attn2.to_v.weight", &e->kv_all, C, c.context_dim, s.kv_off + hp, s.d, s.dpad,
                0);
@@ -517,9 +580,9 @@ static int register_weights(dfb_unet* e) {
       const std::string wn = tb + ".ff.net.0.proj.weight", bn = tb + ".ff.net.0.proj.bias";
       reg(e, wn, [=](const float* src, const int64_t* sh, int nd) -> int {
         if (!shape_is(sh, nd, {2 * C4, C})) return bad_shape(wn);
-        pack_rows_kernel<<<nblk((long)C4 * C), 256>>>(src, g->w, C4, C, 64, 128, 0, 0, C);
-        pack_rows_kernel<<<nblk((long)C4 * C), 256>>>(src + (size_t)C4 * C, g->w, C4, C, 64, 128, 64,
-                                                      0, C);
+        pack_rows_f32_kernel<<<nblk((long)C4 * C), 256>>>(src, g->stage, C4, C, 64, 128, 0, 0, C);
+        pack_rows_f32_kernel<<<nblk((long)C4 * C), 256>>>(src + (size_t)C4 * C, g->stage, C4, C, 64, 128, 64,
+                                                          0, C);
         return cudaGetLastError() == cudaSuccess ? 0 : DFB_E_CUDA;
       });
       reg(e, bn, [=](const float* src, const int64_t* sh, int nd) -> int {
@@ -566,7 +629,8 @@ struct Builder {
   int B;
   const int* rowvec_row = nullptr;  // table mode: device step counter selecting the emb row
   bool dry;  // first pass: only measure scratch requirements
-  size_t need16 = 0, need32 = 0;
+  size_t need16 = 0, need32 = 0, need_st = 0;
+  float2* stats[2] = {nullptr, nullptr};   // per-(row, N-tile) LayerNorm partials, see IGemmEpilogue::stats_out
   __half* a16[4] = {nullptr, nullptr, nullptr, nullptr};
   float* t32[3] = {nullptr, nullptr, nullptr};
   int rc = 0;
@@ -578,28 +642,30 @@ struct Builder {
   void use16(size_t n) { need16 = std::max(need16, n); }
   void use32(size_t n) { need32 = std::max(need32, n); }
 
-  void gemm(const __half* A, const Lin& lin, const IGemmGeom& g, IGemmEpilogue ep) {
-    if (rc) return;
-    if (ep.bias == nullptr && ep.act != ACT_GEGLU) ep.bias = lin.b;
-    if (ep.act == ACT_GEGLU) ep.bias = lin.b;
-    {
-      // every GEMM output lands in one of the shared scratch / stream buffers: size them for it
-      const size_t rows = (size_t)g.B * g.T * g.H * g.W;
-      if (ep.out_f32) use32(rows * ep.ldo);
-      if (ep.out_f16) use16(rows * ep.ldo);
-      use16(rows * g.C);
+  // returns the number of N tiles of the launch (the consumer of a folded LayerNorm needs its producer's)
+  int gemm(const __half* A, const Lin& lin, const IGemmGeom& g, IGemmEpilogue ep) {
+    if (rc) return 0;
+    if (ep.ln_stats == nullptr) {
+      if (ep.bias == nullptr && ep.act != ACT_GEGLU) ep.bias = lin.b;
+      if (ep.act == ACT_GEGLU) ep.bias = lin.b;
     }
+    // every GEMM output lands in one of the shared scratch / stream buffers: size them for it
+    const size_t rows = (size_t)g.B * g.T * g.H * g.W;
+    if (ep.out_f32) use32(rows * ep.ldo);
+    if (ep.out_f16) use16(rows * ep.ldo);
+    use16(rows * g.C);
     IGemmPlan ip;
     if (dry) {
       // plan with dummy (aligned, non-null) pointers just to learn tiling / workspace needs
       static __half* dummy = reinterpret_cast<__half*>(0x1000);
       IGemmEpilogue e2 = ep;
       int r = igemm_plan(&ip, dummy, dummy, lin.N, g, e2, 0);
-      if (r) { rc = r; return; }
-      return;
+      if (r) { rc = r; return 0; }
+      if (ep.stats_out) need_st = std::max(need_st, rows * (size_t)ip.tiles_n);
+      return ip.tiles_n;
     }
     int r = igemm_plan(&ip, A, lin.w, lin.N, g, ep, 0);
-    if (r) { rc = r; return; }
+    if (r) { rc = r; return 0; }
     auto sp = std::make_shared<IGemmPlan>(ip);
     // link the previous GEMM to this one's weights (L2 prefetch of the next layer, see igemm kernel)
     if (prev_gemm && (size_t)lin.N * ip.K * 2 >= ((size_t)1 << 20) && !no_prefetch) {
@@ -608,6 +674,7 @@ struct Builder {
     }
     prev_gemm = sp;
     plan->ops.push_back([sp](cudaStream_t s) { return igemm_launch(*sp, s); });
+    return ip.tiles_n;
   }
   void op(std::function<int(cudaStream_t)> f) {
     if (rc || dry) return;
@@ -692,13 +759,34 @@ struct Builder {
         return groupnorm_launch(xin, C, nullptr, 0, Bc, L, n.g, n.b, 1e-6f, 0, A0, nullptr, st);
       });
     }
-    gemm(A0, s.proj_in, g, ep_f32(x0, C));
-    // --- self-attention
+    const bool fold = e->ln_fold;
+    __half* A3 = a16[3];
+    // LayerNorm folded into the consuming GEMM (ln_fold_kernel): the producer of x writes its fp16 copy and
+    // per-(row, N-tile) partial statistics, the consumer applies rstd / mean in its epilogue -- no LayerNorm
+    // launch, and the consumer's weight prefetch overlaps the producer instead of a 2.5 us norm kernel
+    auto ln_consumer = [&](IGemmEpilogue ep, const Lin& lin, int which, int tiles) {
+      ep.bias = lin.t;
+      ep.ln_stats = stats[which];
+      ep.ln_tiles = tiles;
+      ep.ln_inv_c = 1.0f / (float)C;
+      ep.ln_eps = 1e-5f;
+      ep.ln_s = lin.s;
+      return ep;
+    };
+    int tiles0 = 0;
     {
+      IGemmEpilogue ep = ep_f32(x0, C);
+      if (fold) { ep.out_f16 = A3; ep.stats_out = stats[0]; }
+      tiles0 = gemm(A0, s.proj_in, g, ep);
+    }
+    // --- self-attention
+    if (fold) {
+      gemm(A3, s.qkv, g, ln_consumer(ep_f16(A1, 3 * hp), s.qkv, 0, tiles0));
+    } else {
       const Norm n = s.ln1;
       op([=](cudaStream_t st) { return layernorm_launch(x0, M, C, n.g, n.b, 1e-5f, A0, st); });
+      gemm(A0, s.qkv, g, ep_f16(A1, 3 * hp));
     }
-    gemm(A0, s.qkv, g, ep_f16(A1, 3 * hp));
     {
       const int heads = s.heads, d = s.d, dpad = s.dpad;
       op([=](cudaStream_t st) {
@@ -706,13 +794,20 @@ struct Builder {
                                 d, dpad, scale, st);
       });
     }
-    gemm(A2, s.out1, g, ep_f32(x1, C, x0, C));
-    // --- cross-attention against the pre-computed context K/V
+    int tiles1 = 0;
     {
+      IGemmEpilogue ep = ep_f32(x1, C, x0, C);
+      if (fold) { ep.out_f16 = A0; ep.stats_out = stats[1]; }   // (A0: the GroupNorm output is dead)
+      tiles1 = gemm(A2, s.out1, g, ep);
+    }
+    // --- cross-attention against the pre-computed context K/V
+    if (fold) {
+      gemm(A0, s.q2, g, ln_consumer(ep_f16(A1, hp), s.q2, 1, tiles1));
+    } else {
       const Norm n = s.ln2;
       op([=](cudaStream_t st) { return layernorm_launch(x1, M, C, n.g, n.b, 1e-5f, A0, st); });
+      gemm(A0, s.q2, g, ep_f16(A1, hp));
     }
-    gemm(A0, s.q2, g, ep_f16(A1, hp));
     {
       const int heads = s.heads, d = s.d, dpad = s.dpad, kvld = e->kv_all.N, off = s.kv_off;
       dfb_unet* eng = e;
@@ -723,22 +818,26 @@ struct Builder {
       });
     }
     static const bool fuse_ffproj = getenv("DFB_NO_FFPROJ") == nullptr;
+    int tiles2 = 0;
     {
       IGemmEpilogue ep = ep_f32(x0, C, x1, C);  // x2 -> x0 buffer (old x0 is dead)
-      if (fuse_ffproj) ep.out_f16 = a16[3];      // + the fp16 copy the merged ff/proj GEMM reads
-      gemm(A2, s.out2, g, ep);
+      if (fuse_ffproj || fold) ep.out_f16 = A3;  // + the fp16 copy the GEGLU / merged ff-proj GEMMs read
+      if (fold) ep.stats_out = stats[0];
+      tiles2 = gemm(A2, s.out2, g, ep);
     }
     // --- GEGLU feed-forward
-    {
+    if (fold) {
+      gemm(A3, s.geglu, g, ln_consumer(ep_f16(A1, 4 * C, ACT_GEGLU), s.geglu, 0, tiles2));
+    } else {
       const Norm n = s.ln3;
       op([=](cudaStream_t st) { return layernorm_launch(x0, M, C, n.g, n.b, 1e-5f, A0, st); });
+      gemm(A0, s.geglu, g, ep_f16(A1, 4 * C, ACT_GEGLU));
     }
-    gemm(A0, s.geglu, g, ep_f16(A1, 4 * C, ACT_GEGLU));
     if (fuse_ffproj) {
       // ff.net[2] and proj_out merged (see fuse_ffproj_kernel): [h | x2] x [Wp Wf | Wp]^T + b' + x_in
       IGemmGeom gf = gemm_geom(M, 4 * C);
       gf.C2 = C;
-      gf.A2 = a16[3];
+      gf.A2 = A3;
       gemm(A1, s.ffproj, gf, ep_f32(out, C, xin, C));
     } else {
       gemm(A1, s.ffout, gemm_geom(M, 4 * C), ep_f16(A2, C, ACT_NONE, x0, C));
@@ -789,7 +888,7 @@ static int build_plan(dfb_unet* e, int B, Plan** out, bool emb_table = false) {
     return p;
   };
 
-  size_t s_need16 = 0, s_need32 = 0;
+  size_t s_need16 = 0, s_need32 = 0, s_need_st = 0;
   for (int pass = 0; pass < 2; ++pass) {
     Builder b;
     b.e = e; b.plan = plan.get(); b.B = B; b.dry = (pass == 0);
@@ -807,6 +906,8 @@ static int build_plan(dfb_unet* e, int B, Plan** out, bool emb_table = false) {
         b.t32[i] = reinterpret_cast<float*>((uintptr_t)0x10000 * (i + 4));
         hbuf[i] = reinterpret_cast<float*>((uintptr_t)0x10000 * (i + 7));
       }
+      b.stats[0] = reinterpret_cast<float2*>((uintptr_t)0x10000 * 14);
+      b.stats[1] = reinterpret_cast<float2*>((uintptr_t)0x10000 * 15);
       t16a = reinterpret_cast<__half*>((uintptr_t)0x10000 * 10);
       t16b = reinterpret_cast<__half*>((uintptr_t)0x10000 * 11);
       emb_all = reinterpret_cast<float*>((uintptr_t)0x10000 * 12);
@@ -818,6 +919,10 @@ static int build_plan(dfb_unet* e, int B, Plan** out, bool emb_table = false) {
         b.t32[i] = (float*)palloc(s_need32 * sizeof(float));
         hbuf[i] = (float*)palloc(s_need32 * sizeof(float));
         if (!b.a16[i] || !b.t32[i] || !hbuf[i]) { set_error("plan: cudaMalloc failed"); return DFB_E_CUDA; }
+      }
+      for (int i = 0; i < 2; ++i) {
+        b.stats[i] = (float2*)palloc(std::max<size_t>(s_need_st, 1) * sizeof(float2));
+        if (!b.stats[i]) { set_error("plan: cudaMalloc failed"); return DFB_E_CUDA; }
       }
       t16a = (__half*)palloc((size_t)B * std::max(mc, td) * sizeof(__half));
       t16b = (__half*)palloc((size_t)B * td * sizeof(__half));
@@ -954,6 +1059,7 @@ static int build_plan(dfb_unet* e, int B, Plan** out, bool emb_table = false) {
     if (b.dry) {
       s_need16 = b.need16;
       s_need32 = b.need32;
+      s_need_st = b.need_st;
     }
   }
   *out = plan.get();
@@ -962,9 +1068,21 @@ static int build_plan(dfb_unet* e, int B, Plan** out, bool emb_table = false) {
 }
 
 static int run_plan(dfb_unet* e, Plan* p, cudaStream_t s) {
+  static const bool dbg_sync = getenv("DFB_DEBUG_SYNC") != nullptr;  // diagnostics: find the faulting launch
+  int idx = 0;
   for (auto& f : p->ops) {
     int r = f(s);
     if (r) return r;
+    if (dbg_sync) {
+      cudaError_t ce = cudaStreamSynchronize(s);
+      if (ce != cudaSuccess) {
+        set_error("op " + std::to_string(idx) + " (" + g_note.kind + " M=" + std::to_string(g_note.M) + " N=" +
+                  std::to_string(g_note.N) + " K=" + std::to_string(g_note.K) + " splits=" + std::to_string(g_note.splits) +
+                  ") failed: " + cudaGetErrorString(ce));
+        return DFB_E_CUDA;
+      }
+    }
+    ++idx;
   }
   e->last_launches += (long long)p->ops.size();
   return 0;
@@ -1121,6 +1239,14 @@ int dfb_unet_finalize(dfb_handle h) {
     return DFB_E_STATE;
   }
   cudaSetDevice(h->device);
+  h->ln_fold = (getenv("DFB_NO_LNFOLD") == nullptr);
+  for (auto& s : h->sts) {
+    const int f = h->ln_fold ? 1 : 0;
+    ln_fold_kernel<<<s.qkv.N, 128>>>(s.qkv.stage, s.ln1.g, s.ln1.b, nullptr, s.qkv.K, f, s.qkv.w, s.qkv.s, s.qkv.t);
+    ln_fold_kernel<<<s.q2.N, 128>>>(s.q2.stage, s.ln2.g, s.ln2.b, nullptr, s.q2.K, f, s.q2.w, s.q2.s, s.q2.t);
+    ln_fold_kernel<<<s.geglu.N, 128>>>(s.geglu.stage, s.ln3.g, s.ln3.b, s.geglu.b, s.geglu.K, f, s.geglu.w, s.geglu.s,
+                                       s.geglu.t);
+  }
   for (auto& s : h->sts) {
     const int C = s.C, C4 = 4 * C;
     fuse_ffproj_kernel<<<dim3((C4 + 31) / 32, C / 32), 1024>>>(s.proj_out.w, s.ffout.w, s.ffout.b, s.proj_out.b, C,

@@ -129,6 +129,19 @@ int dfb_unet_destroy(dfb_handle h);
 int dfb_gemm(const void* a_f16_dev, const void* w_f16_dev, int M, int N, int K, const float* bias_dev,
              const float* residual_dev, int act, float* out_f32_dev, void* out_f16_dev, int splits,
              void* stream);
+/* LayerNorm folded into the consuming Linear (attention_openai.py:211-215: attn(norm(x)), ff(norm(x))).
+ * Producer side: dfb_gemm_stats is dfb_gemm that also writes, per output row and per N-tile of the launch,
+ * the partial (sum, sum of squares) of its fp32 outputs to stats_dev [M, *tiles_n_out] (float2); tiles_n_out
+ * is a host int the call fills in.  Consumer side: dfb_gemm_ln computes
+ *   out = act( rstd_m * (A . W'^T) - rstd_m * mu_m * ln_s[n] + t[n] )
+ * with A the raw fp16 x, W' = fp16(gamma . W), ln_s[n] = sum_k W'[n,k], t[n] = sum_k beta_k W[n,k] + b[n],
+ * and (mu_m, rstd_m) merged from ln_stats_dev [M, ln_tiles] over C = K columns with eps ln_eps. */
+int dfb_gemm_stats(const void* a_f16_dev, const void* w_f16_dev, int M, int N, int K, const float* bias_dev,
+                   const float* residual_dev, float* out_f32_dev, void* out_f16_dev, int splits,
+                   void* stats_dev, int* tiles_n_out, void* stream);
+int dfb_gemm_ln(const void* a_f16_dev, const void* w_f16_dev, int M, int N, int K, const float* t_dev,
+                const float* ln_s_dev, const void* ln_stats_dev, int ln_tiles, float ln_eps, int act,
+                float* out_f32_dev, void* out_f16_dev, int splits, void* stream);
 /* 3x3 / stride 1 / pad 1 convolution as implicit GEMM; a: fp16 NHWC [B,H,W,C], w: fp16 [N, 9*C]
  * with k = (ky*3+kx)*C + c; rowvec: optional fp32 [B,N] added per sample (timestep embedding,
  * openai_unetmodel.py:263-272); residual: optional fp32 NHWC [B,H,W,N]. */

@@ -93,6 +93,60 @@ def test_gemm_geglu(splits):
     assert rel_l2(out.float(), ref) < 1e-3
 
 
+# LayerNorm folded into the consuming GEMM: producer (x = A.Wp^T + b + res, fp32 + fp16 copy + per-tile row
+# statistics) followed by consumer (LN(x).W^T + b as rstd*(x16.W'^T) - rstd*mu*s + t); the UNet's
+# (tokens, C) call sites incl. the M = 32 level (3/4 of the tile rows outside the tensor), split-K both ways
+@pytest.mark.parametrize("M,C,N,act,sp_p,sp_c", [
+    (2048, 320, 1152, 0, 0, 0), (512, 640, 1920, 0, 0, 0), (128, 1280, 3840, 0, 0, 0), (32, 1280, 3840, 0, 0, 0),
+    (32, 1280, 1280, 0, 5, 4), (2048, 320, 2560, 2, 1, 1), (128, 1280, 10240, 2, 0, 0), (32, 1280, 10240, 2, 0, 0),
+    (200, 64, 192, 0, 1, 2),
+])
+def test_gemm_layernorm_fold(M, C, N, act, sp_p, sp_c):
+    import ctypes as Ct
+    g = torch.Generator(device="cpu").manual_seed(M + C + N + act)
+    a = torch.randn(M, C, generator=g).to(DEV).half()
+    wp = (torch.randn(C, C, generator=g) / math.sqrt(C)).to(DEV).half()
+    bp = torch.randn(C, generator=g).to(DEV)
+    res = (torch.randn(M, C, generator=g) + 0.5).to(DEV)
+    gamma = (1.0 + 0.3 * torch.randn(C, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(C, generator=g)).to(DEV)
+    w = (torch.randn(N, C, generator=g) / math.sqrt(C)).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    lib = L.lib()
+    # ---- producer
+    x32 = torch.full((M, C), float("nan"), device=DEV)
+    x16 = torch.zeros(M, C, device=DEV, dtype=torch.float16)
+    stats = torch.zeros(M, 64, 2, device=DEV)
+    tiles = Ct.c_int(0)
+    L.check(lib.dfb_gemm_stats(L.ptr(a), L.ptr(wp), M, C, C, L.ptr(bp), L.ptr(res), L.ptr(x32), L.ptr(x16), sp_p,
+                               L.ptr(stats), Ct.byref(tiles), L.cur_stream()), "dfb_gemm_stats")
+    sync()
+    x_ref = a.float() @ wp.float().t() + bp + res
+    assert rel_l2(x32, x_ref) < 2e-6
+    st = stats.view(-1)[: M * tiles.value * 2].view(M, tiles.value, 2)
+    assert rel_l2(st[..., 0].sum(1), x32.sum(1)) < 1e-5 and rel_l2(st[..., 1].sum(1), (x32 * x32).sum(1)) < 1e-5
+    # ---- consumer: folded weights as engine.cu's ln_fold_kernel builds them
+    wf = (gamma[None, :] * w).half()
+    s_n = wf.float().sum(1)
+    t_n = (w * beta[None, :]).sum(1) + b
+    if act == 2:   # GEGLU: value | gate interleaved per 128-column tile
+        h = N // 2
+        il = lambda v: torch.cat([v[:h].view(h // 64, 64, *v.shape[1:]), v[h:].view(h // 64, 64, *v.shape[1:])], 1).reshape(v.shape).contiguous()
+        wf, s_n, t_n = il(wf), il(s_n), il(t_n)
+    No = N // 2 if act == 2 else N
+    out = torch.full((M, No), float("nan"), device=DEV, dtype=torch.float16)
+    L.check(lib.dfb_gemm_ln(L.ptr(x16), L.ptr(wf), M, N, C, L.ptr(t_n), L.ptr(s_n), L.ptr(st.contiguous()), tiles.value,
+                            1e-5, act, None, L.ptr(out), sp_c, L.cur_stream()), "dfb_gemm_ln")
+    sync()
+    y = F.layer_norm(x_ref, (C,), gamma, beta, 1e-5) @ w.t() + b
+    if act == 2:
+        v, gate = y.chunk(2, dim=-1)
+        y = v * F.gelu(gate)
+    err = rel_l2(out.float(), y)
+    print(f"\n[ln-fold] M={M} C={C} N={N} act={act}: rel-L2 {err:.2e}")
+    assert torch.isfinite(out.float()).all() and err < 1.5e-3
+
+
 def conv3x3(a16_nhwc, w_oihw16, bias=None, rowvec=None, residual=None, splits=0):
     B, H, W, C = a16_nhwc.shape
     N = w_oihw16.shape[0]
