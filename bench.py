@@ -118,23 +118,140 @@ def cpu_reference_step_seconds(steps, warmup, state_dict=None):
 
 
 def run_reference(args):
+    """Reference arm: the reference algorithm's CPU path (oracle port; the reference is pure Python/PyTorch and
+    only importable in the build container) on all host cores.  One timed "step" = ONE of the 25 DDIM steps of
+    config 2 (UNet forward at B_eff = 2 + CFG update) -- a bounded sample of the workload, every DDIM step costs
+    the same; `ms_per_step` is the measured time of those steps, `value` = 1 / (25 x step seconds)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 40)), max(1, min(args.warmup, 3))
+    steps, warmup = max(1, min(args.steps, 40)), max(0, min(args.warmup, 10))
     sec, cores = cpu_reference_step_seconds(steps, warmup)
     value = 1.0 / (DDIM_STEPS * sec)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3 * DDIM_STEPS, "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "config 2: DDIM-25, CFG 4.5, B=1 clip (B_eff=2), UNet 859.5M, latent 4x16x64, ctx 32x768",
-                   "timed": "each step = 1 of the 25 DDIM steps (UNet fwd at B_eff=2 + update); value = 1/(25*step_s)"},
+                   "timed": "each step = ONE of the 25 DDIM steps (UNet fwd at B_eff=2 + update); ms_per_step is per "
+                            "DDIM step; value = 1/(25 * step_s) latents/s (x25: one latent = 25 such steps)",
+                   "ddim_steps_per_latent": DDIM_STEPS},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{steps} single DDIM steps (UNet fwd B_eff=2 + update), fp32 torch CPU, {cores} threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def gpu_reference_block(sd_cuda, x_T, cond, unc, dev):
+    """SURVEY 8(d) 'GPU reference beside it': the reference's algorithm (oracle port = the same torch ops the
+    reference modules issue) in eager PyTorch on THIS B200 -- fp32 with TF32 off, with TF32 on (the
+    reference's de-facto default for convs), and the TF32 step captured as one CUDA graph (no launch
+    overhead).  One DDIM step with CFG at B_eff = 2 per timed step; latents/s = 1 / (25 x step_s)."""
+    import torch
+    from oracle import ddim_oracle, unet_oracle  # measured baseline leg, not the product path
+    cfg = unet_oracle.DIFF_FOLEY_UNET
+    c = ddim_oracle.ddim_coefficients(DDIM_STEPS)
+    ts = torch.full((2,), int(c["timesteps"][0]), dtype=torch.long, device=dev)
+    xx, cc = torch.cat([x_T[:1], x_T[:1]]), torch.cat([unc[:1], cond[:1]])
+
+    def step():
+        e = unet_oracle.unet_forward(sd_cuda, cfg, xx, ts, cc)
+        return e[:1] + CFG_SCALE * (e[1:] - e[:1])
+
+    def time_it(fn, n=10, w=3):
+        for _ in range(w):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    out = {"what": "oracle port of the reference UNet + CFG combine, eager torch on the same B200, one DDIM step "
+                   "at B_eff=2 per timed step; latents/s = 1/(25*step)", "unit": UNIT}
+    old_mm, old_cudnn = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        ms = time_it(step)
+        out["eager_fp32"] = {"step_ms": ms, "value": 1e3 / (DDIM_STEPS * ms)}
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
+        ms = time_it(step)
+        out["eager_tf32"] = {"step_ms": ms, "value": 1e3 / (DDIM_STEPS * ms)}
+        try:
+            g = torch.cuda.CUDAGraph()
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                step()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    step()
+                ms = time_it(g.replay)
+            out["graph_tf32"] = {"step_ms": ms, "value": 1e3 / (DDIM_STEPS * ms)}
+        except Exception as ex:  # capture is best effort: the eager numbers stand on their own
+            out["graph_tf32"] = {"error": str(ex)[:200]}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old_mm, old_cudnn
+    return out
+
+
+def config3_block(ldm, unet, dev, timed):
+    """BASELINE config 3: B = 8 clips, DDIM-25, CFG 4.5 + double-guidance classifier (scale 50) on one B200:
+    UNet at B_eff = 16 per step + classifier forward/backward on the 8 latents (ddim.py:344-396)."""
+    import torch
+    from diff_foley_b200.classifier import AlignmentClassifierDoubleGuidanceB200
+    from diff_foley_b200.weights import randomize_parameters_
+    B = 8
+    g = torch.Generator().manual_seed(4321)
+    x_T = torch.randn(B, 4, 16, 64, generator=g).to(dev)
+    feats = torch.nn.functional.normalize(torch.randn(B, 32, 512, generator=g), dim=-1).to(dev)
+    cond = ldm.get_learned_conditioning(feats)
+    unc = torch.zeros_like(cond)
+    out = {"workload": "config 3: 8 clips, DDIM-25, CFG 4.5 + classifier guidance 50, single B200", "unit": UNIT}
+
+    def plain():
+        ldm.sample_log_diff_sampler(cond, B, "DDIM", DDIM_STEPS, unconditional_guidance_scale=CFG_SCALE,
+                                    unconditional_conditioning=unc, x_T=x_T)
+    ms = timed(plain, 3, 2)
+    out["cfg_only_B8"] = {"value": B * 3 / (ms / 1e3), "ms_per_8_latents": ms / 3, "unet_step_ms": ms / 3 / DDIM_STEPS}
+    clf = AlignmentClassifierDoubleGuidanceB200().to(dev)
+    randomize_parameters_(clf, seed=9)
+
+    def guided():
+        ldm.sample_log_with_classifier_diff_sampler(cond, feats, B, "DDIM", DDIM_STEPS,
+                                                    unconditional_guidance_scale=CFG_SCALE,
+                                                    unconditional_conditioning=unc, classifier=clf,
+                                                    classifier_guide_scale=50.0, x_T=x_T)
+    ms = timed(guided, 2, 1)
+    out["value"] = B * 2 / (ms / 1e3)
+    out["ms_per_8_latents"] = ms / 2
+    out["classifier"] = clf.backend_description()
+    return out
+
+
+def config4_block(ldm, unet, dev, world, timed, dist):
+    """BASELINE config 4 scheme at 8 clips per GPU (64 clips on 8 GPUs): (clip, branch) units sharded over the
+    ranks, per-step NCCL eps all-gather captured inside the step graph (dfb_ddim_sample with a communicator)."""
+    import torch
+    from diff_foley_b200.parallel import sharded_ddim_sample
+    B = 8 * world
+    g = torch.Generator().manual_seed(777)
+    x_T = torch.randn(B, 4, 16, 64, generator=g).to(dev)
+    feats = torch.nn.functional.normalize(torch.randn(B, 32, 512, generator=g), dim=-1).to(dev)
+    cond = ldm.get_learned_conditioning(feats)
+    unc = torch.zeros_like(cond)
+
+    def run():
+        sharded_ddim_sample(ldm, x_T, cond, unc, CFG_SCALE, DDIM_STEPS)
+    ms = timed(run, 3, 2)
+    return {"workload": f"config 4: {B} clips on {world} GPUs (8 clips = 16 units per GPU), DDIM-25, CFG 4.5, eps "
+                        "all-gather in the step graph", "value": B * 3 / (ms / 1e3), "unit": UNIT,
+            "ms_per_batch": ms / 3, "step_ms": ms / 3 / DDIM_STEPS, "global_clips": B}
 
 
 # ------------------------------------------------------------------------------------------ ours
@@ -158,7 +275,7 @@ def run_ours(args):
     C = args.clips_per_gpu
     B_global = C * world
 
-    unet = UNetModelB200(**FULL, max_batch=max(2 * C, 2), max_context_len=40).to(dev)
+    unet = UNetModelB200(**FULL, max_batch=max(2 * C, 16), max_context_len=40).to(dev)
     randomize_parameters_(unet, seed=7)
     ldm = LatentDiffusionB200(unet).to(dev)
     randomize_parameters_(ldm.cond_stage_model, seed=8)
@@ -216,9 +333,7 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
     ms_total = timed(sample_resident, K, W)
-    launches = unet.last_launch_count()          # fused path: launches of one whole sampling call
-    if world > 1:                                # sharded path: one captured forward + gather/update per step
-        launches = (launches + 3) * DDIM_STEPS
+    launches = unet.last_launch_count()          # fused path (single-GPU and sharded): launches of one whole call
     clk = clocks.stop() if rank == 0 else None
     ms_e2e = timed(sample_e2e, K, 1)
     value = B_global * K / (ms_total / 1e3)
@@ -231,10 +346,14 @@ def run_ours(args):
         prof = unet.profile(torch.cat([x_T[:C], x_T[:C]]), torch.full((2 * C,), 961, device=dev, dtype=torch.long),
                             torch.cat([unc[:C], cond[:C]]), iters=5)
         ig = [p for p in prof if p["kind"].startswith("igemm")]
-        ig_ms = sum(p["ms"] for p in ig)
+        ig_ms_evt = sum(p["ms"] for p in ig)
         all_ms = sum(p["ms"] for p in prof)
-        w_bytes = sum(2.0 * p["N"] * p["K"] for p in ig)       # fp16 weights, streamed once per forward
-        ig_bytes = sum(p["bytes"] for p in ig)
+        # algorithmic bytes: every fp16 weight byte once + the fp16 A operand once + the output once
+        # at 16 bit; fp32 residual-stream traffic stays in L2 at B_eff = 2 and is NOT counted
+        w_bytes = sum(2.0 * p["N"] * p["K"] for p in ig)
+        a_bytes = sum(2.0 * p["M"] * (p["K"] / (9 if p["kind"] == "igemm_conv3x3" else 1)) for p in ig)
+        o_bytes = sum(2.0 * p["M"] * p["N"] for p in ig)
+        ig_bytes = w_bytes + a_bytes + o_bytes
         ig_flops = sum(p["flops"] for p in ig)
         by_kind = {}
         for p in prof:
@@ -243,18 +362,20 @@ def run_ours(args):
         # The per-launch profile puts an event between consecutive kernels, which adds a few us to each;
         # the kernel's SHARE of the forward is robust to that, so its time inside the real (graph-replayed)
         # step is taken as share x measured UNet step time.
-        ig_ms_raw = ig_ms
-        ig_ms = (ig_ms / all_ms) * (ms_total / K / DDIM_STEPS)
+        share = ig_ms_evt / all_ms if all_ms else 0.0
+        step_ms = ms_total / K / DDIM_STEPS
+        ig_ms = share * step_ms
         ach_gbs = ig_bytes / (ig_ms / 1e3) / 1e9
         ach_tf = ig_flops / (ig_ms / 1e3) / 1e12
         hbm_bound = (ig_bytes / pk["hbm"] / 1e9) >= (ig_flops / pk["tf_sust"] / 1e12)
-        # DRAM traffic of the same igemm launches from the committed ncu pass (B_eff = 2 only); null otherwise
+        # DRAM traffic of the same igemm launches from the committed ncu pass of THIS build (B_eff = 2 only)
         traffic, traffic_src = None, None
-        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_igemm_dram_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r2_igemm_dram_traffic.json")
         if C == 1 and os.path.exists(tpath):
             tj = json.load(open(tpath))
             traffic = tj["dram_bytes_read_per_forward"] + tj["dram_bytes_write_per_forward"]
             traffic_src = tj["source"]
+        weights_total = 1.719e9   # 859.5 M parameters at 16 bit
         roofline = {
             "kernel": "igemm_tcgen05_kernel (all Linear / 1x1 / 3x3 conv launches of one UNet forward)",
             "bound": "hbm" if hbm_bound else "tensor",
@@ -264,13 +385,18 @@ def run_ours(args):
             "frac": (ach_gbs / pk["hbm"]) if hbm_bound else (ach_tf / pk["tf_sust"]),
             "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk["src"],
             "launches_per_forward": len(ig), "kernel_ms_per_forward": ig_ms,
-            "kernel_ms_per_forward_event_profile": ig_ms_raw, "all_kernels_ms_per_forward_event_profile": all_ms,
-            "how": f"algorithmic bytes (or flops) of the {len(ig)} igemm launches of one UNet forward / (igemm share of the per-launch event profile x graph-timed UNet step)",
-            "share_of_step": ig_ms / all_ms if all_ms else None,
+            "share_of_step": share,
+            "how": f"algorithmic bytes (or flops) of the {len(ig)} igemm launches of one UNet forward / (igemm share of the "
+                   "per-launch event profile x graph-timed UNet step)",
             "algorithmic_bytes_per_forward": ig_bytes, "weight_bytes_per_forward": w_bytes,
             "algorithmic_flops_per_forward": ig_flops,
             "achieved_tflops": ach_tf, "achieved_gbs": ach_gbs,
-            "by_kind_ms": {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in sorted(by_kind.items())},
+            "whole_step": {"unet_step_ms": step_ms,
+                           "hbm_bound_ms": weights_total / pk["hbm"] / 1e6,
+                           "tensor_bound_ms": 2 * C * UNET_GFLOP_PER_SAMPLE / pk["tf_sust"],
+                           "frac_of_bound": max(weights_total / pk["hbm"] / 1e6,
+                                                2 * C * UNET_GFLOP_PER_SAMPLE / pk["tf_sust"]) / step_ms},
+            "by_kind_ms_event_profile": {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in sorted(by_kind.items())},
         }
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
@@ -302,6 +428,36 @@ def run_ours(args):
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
+        if world == 1 and C == 1 and not args.no_extras:
+            # ---- the reference's eager-PyTorch path on this GPU (SURVEY 8d "bar to beat")
+            try:
+                sd_cuda = {k: v.detach().float() for k, v in unet.state_dict().items()}
+                line["gpu_reference"] = gpu_reference_block(sd_cuda, x_T, cond, unc, dev)
+                del sd_cuda
+            except Exception as ex:
+                line["gpu_reference"] = {"error": str(ex)[:300]}
+            # ---- drop-in path: the reference-style host loop (apply_model per step + dfb_ddim_step), i.e. what
+            # a user gets from only swapping unet_config.target and keeping the reference sampler's structure
+            def sample_hostloop():
+                ldm.sample_log_diff_sampler(cond, 1, "DDIM", DDIM_STEPS, unconditional_guidance_scale=CFG_SCALE,
+                                            unconditional_conditioning=unc, x_T=x_T, callback=lambda i: None)
+            ms_h = timed(sample_hostloop, 3, 1)
+            line["dropin_host_loop"] = {"value": 3 / (ms_h / 1e3), "unit": UNIT, "ms_per_latent": ms_h / 3,
+                                        "what": "DDIMSamplerB200 host loop (UNetModelB200.forward per step incl. K/V "
+                                                "recompute + dfb_ddim_step), no CUDA graph"}
+        torch.cuda.empty_cache()
+    # ---- BASELINE configs 3 and 4 as sub-records (the headline stays config 2 / weak scaling)
+    extras = {}
+    if not args.no_extras and C == 1:
+        try:
+            if world == 1:
+                extras["config3"] = config3_block(ldm, unet, dev, timed)
+            else:
+                extras["config4"] = config4_block(ldm, unet, dev, world, timed, dist)
+        except Exception as ex:
+            extras["error"] = str(ex)[:300]
+    if rank == 0:
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -382,6 +538,7 @@ def main():
     ap.add_argument("--clips-per-gpu", type=int, default=1)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the gpu_reference / drop-in / config 3 / config 4 sub-records")
     ap.add_argument("--workload", default="ddim", choices=["ddim", "cavp"])
     args = ap.parse_args()
     if args.workload == "cavp":

@@ -53,7 +53,10 @@ SIGNATURES = {
     "dfb_unet_set_context": (_i, [_vp, _fp, _i, _i, _vp]),
     "dfb_unet_forward": (_i, [_vp, _fp, _i, _vp, _i, _fp, _i, _fp, _i, _vp]),
     "dfb_ddim_sample": (_i, [_vp, _fp, _fp, _fp, _i, _i, _f, _i, _i64p, C.POINTER(_f), C.POINTER(_f),
-                             C.POINTER(_f), C.POINTER(_f), _fp, _vp]),
+                             C.POINTER(_f), C.POINTER(_f), _fp, _fp, _fp, _vp]),
+    "dfb_comm_unique_id": (_i, [_vp]),
+    "dfb_comm_init": (_i, [_vp, _i, _i, _vp]),
+    "dfb_comm_destroy": (_i, [_vp]),
     "dfb_unet_profile": (_i, [_vp, _fp, _i, _vp, _i, _fp, _i, _i, C.POINTER(OpInfo), _i, C.POINTER(_i), _vp]),
     "dfb_unet_trace": (_i, [_vp, _fp, _i, _vp, _i, _fp, _i, C.POINTER(C.c_ulonglong), _i, C.POINTER(_i), _vp]),
     "dfb_debug_igemm_force": (None, [_i, _i]),

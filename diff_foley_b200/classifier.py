@@ -143,17 +143,28 @@ class ClassifierBackboneB200(nn.Module):
         return torch.sigmoid(F.linear(h, self.classifier.weight, self.classifier.bias))
 
 
+# Double_Guidance_Classifier.yaml (inference/config): the 11.45 M-parameter half-UNet
+DIFF_FOLEY_CLASSIFIER_PARAMS = dict(image_size=32, in_channels=4, out_channels=1, model_channels=128,
+                                    attention_resolutions=[2, 4], num_res_blocks=1, channel_mult=[1, 2, 2],
+                                    num_heads=8, use_spatial_transformer=True, transformer_depth=1, context_dim=512,
+                                    use_checkpoint=True, legacy=False)
+
+
 class AlignmentClassifierDoubleGuidanceB200(nn.Module):
     """`.model` / `.cond_model` like the reference wrapper; in inference the raw (un-embedded) CAVP
     features go straight to the backbone (alignment_classifier.py:269-271)."""
 
-    def __init__(self, classifier_params, cond_stage_params=None, scale_factor=0.18215, **ignored):
+    def __init__(self, classifier_params=None, cond_stage_params=None, scale_factor=0.18215, **ignored):
         super().__init__()
         from .ldm import VideoFeatEncoderPosembed
-        self.model = ClassifierBackboneB200(**classifier_params)
+        self.model = ClassifierBackboneB200(**(DIFF_FOLEY_CLASSIFIER_PARAMS if classifier_params is None else classifier_params))
         cs = dict(origin_dim=512, embed_dim=512, seq_len=40) if cond_stage_params is None else cond_stage_params
         self.cond_model = VideoFeatEncoderPosembed(**cs)
         self.register_buffer("scale_factor", torch.tensor(scale_factor))
 
     def forward(self, spec_noisy, video_feat, t):
         return self.model(spec_noisy, context=video_feat, timesteps=t)
+
+    @staticmethod
+    def backend_description():
+        return "torch autograd on the GPU (cuDNN / cuBLAS library kernels) -- forward + backward, see classifier.py"

@@ -179,8 +179,8 @@ int upsample2x_f16_launch(const float* src, __half* dst, int B, int H, int W, in
 // im2col for 3x3 / pad 1 / stride 2: fp32 NHWC [B,H,W,C] -> fp16 [B*(H/2)*(W/2), 9*C]
 int im2col_s2_launch(const float* src, __half* dst, int B, int H, int W, int C,
                      cudaStream_t stream);
-// stem conv: x NCHW fp32 [Bsrc,Cin,H,W] (sample b reads x[b % Bsrc]) -> NHWC fp32 [B,H,W,Cout]
-int stem_conv_launch(const float* x, int Bsrc, int B, int Cin, int H, int W, const float* w,
+// stem conv: x NCHW fp32 [Bsrc,Cin,H,W] (sample b reads x[(b + xoff) % Bsrc]) -> NHWC fp32 [B,H,W,Cout]
+int stem_conv_launch(const float* x, int Bsrc, int xoff, int B, int Cin, int H, int W, const float* w,
                      const float* bias, int Cout, float* out, cudaStream_t stream);
 // head conv: fp16 NHWC [B,H,W,C] (already GN+SiLU'd) -> NCHW fp32 [B,Cout,H,W]
 int head_conv_launch(const __half* a, int B, int H, int W, int C, const float* w,

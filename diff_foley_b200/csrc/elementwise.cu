@@ -148,14 +148,14 @@ int im2col_s2_launch(const float* src, __half* dst, int B, int H, int W, int C, 
 // ---------------------------------------------------------------------------------------------
 // stem: conv3x3(Cin->Cout), pad 1, on the NCHW latent (reference openai_unetmodel.py:519).
 // w is packed [Cin*9, Cout] (k = ci*9 + tap) so consecutive threads (co) read consecutive floats.
-__global__ void stem_conv_kernel(const float* __restrict__ x, int Bsrc, int Cin, int H, int W,
+__global__ void stem_conv_kernel(const float* __restrict__ x, int Bsrc, int xoff, int Cin, int H, int W,
                                  const float* __restrict__ w, const float* __restrict__ bias, int Cout,
                                  float* __restrict__ out) {
   pdl_wait();
   pdl_launch_dependents();
   const int pix = blockIdx.x;  // b*H*W + y*W + x
   const int xq = pix % W, yq = (pix / W) % H, b = pix / (W * H);
-  const int bs = b % Bsrc;
+  const int bs = (b + xoff) % Bsrc;
   extern __shared__ float patch[];  // [Cin*9]
   for (int i = threadIdx.x; i < Cin * 9; i += blockDim.x) {
     const int ci = i / 9, tap = i - ci * 9;
@@ -172,10 +172,10 @@ __global__ void stem_conv_kernel(const float* __restrict__ x, int Bsrc, int Cin,
   }
 }
 
-int stem_conv_launch(const float* x, int Bsrc, int B, int Cin, int H, int W, const float* w,
+int stem_conv_launch(const float* x, int Bsrc, int xoff, int B, int Cin, int H, int W, const float* w,
                      const float* bias, int Cout, float* out, cudaStream_t stream) {
   note("stem_conv", 2.0 * B * H * W * Cin * 9 * Cout, (double)B * H * W * Cout * 4.0);
-  DFB_CUDA_OK(launch_pdl(stem_conv_kernel, dim3(B * H * W), dim3(128), Cin * 9 * sizeof(float), stream, x, Bsrc, Cin, H, W, w, bias,
+  DFB_CUDA_OK(launch_pdl(stem_conv_kernel, dim3(B * H * W), dim3(128), Cin * 9 * sizeof(float), stream, x, Bsrc, xoff, Cin, H, W, w, bias,
                                                                         Cout, out));
   DFB_CUDA_OK(cudaGetLastError());
   return 0;

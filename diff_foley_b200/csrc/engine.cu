@@ -21,11 +21,46 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include "../../include/dfb.h"
 #include "dfb_internal.h"
 #include "dfb_ptx.cuh"
 
 namespace dfb {
+
+// ---- NCCL, bound at run time (dlopen by SONAME: inside a torch process this resolves to the copy torch
+// already loaded, so the library and torch.distributed share one NCCL; a plain C host gets the system one).
+// Only the five entry points the sampler's per-step eps all-gather needs (nccl.h: ncclGetUniqueId,
+// ncclCommInitRank, ncclAllGather, ncclCommDestroy, ncclGetErrorString).
+struct NcclApi {
+  typedef struct { char internal[128]; } UniqueId;
+  int (*GetUniqueId)(UniqueId*) = nullptr;
+  int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+static NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* so = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!so) so = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (so) {
+      api.GetUniqueId = (int (*)(NcclApi::UniqueId*))dlsym(so, "ncclGetUniqueId");
+      api.CommInitRank = (int (*)(void**, int, NcclApi::UniqueId, int))dlsym(so, "ncclCommInitRank");
+      api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(so, "ncclAllGather");
+      api.CommDestroy = (int (*)(void*))dlsym(so, "ncclCommDestroy");
+      api.GetErrorString = (const char* (*)(int))dlsym(so, "ncclGetErrorString");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy && api.GetErrorString;
+    }
+  }
+  return api;
+}
+constexpr int NCCL_FLOAT32 = 7;  // ncclFloat32 (nccl.h)
 
 thread_local LaunchNote g_note = {"none", 0, 0, 0, 0, 0, 1, 0};
 TraceState g_trace;
@@ -240,6 +275,7 @@ struct dfb_unet {
   // per-call pointers (read by the stem / temb / head ops at launch time)
   const float* cur_x = nullptr;
   int cur_x_repeat = 1;
+  int cur_x_nsrc = 0, cur_x_off = 0;  // sharded sampler: local unit j reads x[(j + off) % nsrc] (0 = use x_repeat)
   const void* cur_t = nullptr;
   int cur_t_is_float = 0;
   float* cur_out = nullptr;
@@ -252,21 +288,28 @@ struct dfb_unet {
   std::map<int, std::unique_ptr<Plan>> plans;
   long long last_launches = 0;
 
-  // sampler state
+  // multi-GPU: the library owns its NCCL communicator (SURVEY 8b "Ownership"); one handle = one rank
+  void* comm = nullptr;
+  int rank = 0, world = 1;
+
+  // sampler state: every buffer is engine-owned and sized for the largest call seen so far, so the captured
+  // graph -- which runs on the engine's x / pred_x0 staging buffers, the caller's tensors are copied in and
+  // out -- is reused across calls regardless of the caller's allocator
   struct Sampler {
-    int n_clips = 0, ctx_len = 0, n_steps = 0;
+    int n_clips = 0, ctx_len = 0, table = -1, lo = 0, n_loc = 0;   // what `exec` was captured for
     float cfg_scale = 0.f;
-    float* coefs = nullptr;     // device [S,4]
-    long long* tsteps = nullptr;  // device [S]
-    int* step = nullptr;        // device scalar
-    long long* t_cur = nullptr;   // device [b_eff] (filled per step)
-    float* eps = nullptr;       // device [2B,4,H,W]
-    float* ctx_cat = nullptr;   // device [2B,L,D]
-    float* x_ptr = nullptr;
-    float* px0_ptr = nullptr;
+    float* coefs = nullptr;       // device [MAX_STEPS, 5]
+    long long* tsteps = nullptr;  // device [MAX_STEPS]
+    int* step = nullptr;          // device scalar
+    unsigned int* done = nullptr; // device counter of the update kernel's finished blocks (wraps)
+    long long* t_cur = nullptr;   // device [max_batch] (filled per step, non-table mode)
+    float* eps = nullptr;         // device [2B,4,H,W] of ALL units (all-gathered when sharded)
+    float* ctx_cat = nullptr;     // device [2B,L,D]
+    float* x_buf = nullptr;       // device [B,4,H,W]
+    float* px0_buf = nullptr;
+    size_t cap_lat = 0, cap_ctx = 0;  // capacities (floats) of eps/x_buf/px0_buf (per 2B / B) and ctx_cat
     cudaGraphExec_t exec = nullptr;
     cudaStream_t cap_stream = nullptr;
-    int cap_S = 0;
     // table of SiLU(time_embed(t)) -> all 22 emb_layers for every step of the schedule: the timestep
     // embedding depends on t and the weights only, so the sampler computes it once per schedule (M = S
     // rows through the same GEMMs) instead of 4 launches inside every step; the step's convs pick row
@@ -962,8 +1005,9 @@ static int build_plan(dfb_unet* e, int B, Plan** out, bool emb_table = false) {
       dfb_unet* eng = e;
       const int Bc = B, Cin = c.in_channels, Hc = H, Wc = W;
       b.op([=](cudaStream_t s) {
-        return stem_conv_launch(eng->cur_x, Bc / eng->cur_x_repeat, Bc, Cin, Hc, Wc, eng->stem_w,
-                                eng->stem_b, mc, h, s);
+        const int nsrc = eng->cur_x_nsrc > 0 ? eng->cur_x_nsrc : Bc / eng->cur_x_repeat;
+        return stem_conv_launch(eng->cur_x, nsrc, eng->cur_x_nsrc > 0 ? eng->cur_x_off : 0, Bc, Cin, Hc, Wc,
+                                eng->stem_w, eng->stem_b, mc, h, s);
       });
     }
     int hrot = 0;
@@ -1118,25 +1162,30 @@ __global__ void step_begin_kernel(const long long* __restrict__ tsteps, const in
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) t_cur[i] = tsteps[*step];
 }
-__global__ void step_end_kernel(int* step) {
-  pdl_wait();  // the update kernel reads *step: never run ahead of it
-  pdl_launch_dependents();
-  *step += 1;
-}
-// coefs[step] = {sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), cfg_scale}
+// coefs[step] = {sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), cfg_scale}.  The last block to
+// finish advances the step counter (every block read it before its arrival on `done`, a counter that wraps
+// at gridDim.x): no separate counter kernel.
 __global__ void ddim_update_graph_kernel(float* __restrict__ x, const float* __restrict__ eps,
                                          size_t n, const float* __restrict__ coefs,
-                                         const int* __restrict__ step, float* __restrict__ pred_x0) {
+                                         int* __restrict__ step, unsigned int* __restrict__ done,
+                                         float* __restrict__ pred_x0) {
   pdl_wait();
   pdl_launch_dependents();
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float* c = coefs + 5 * (*step);
-  const float eu = eps[i], ec = eps[n + i];
-  const float e = __fadd_rn(eu, __fmul_rn(c[4], __fsub_rn(ec, eu)));
-  const float x0 = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(c[0], e)), c[1]);
-  x[i] = __fadd_rn(__fmul_rn(c[2], x0), __fmul_rn(c[3], e));
-  if (pred_x0 != nullptr) pred_x0[i] = x0;
+  const int st = *step;
+  const float* c = coefs + 5 * st;
+  const float c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float eu = eps[i], ec = eps[n + i];
+    const float e = __fadd_rn(eu, __fmul_rn(c4, __fsub_rn(ec, eu)));
+    const float x0 = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(c0, e)), c1);
+    x[i] = __fadd_rn(__fmul_rn(c2, x0), __fmul_rn(c3, e));
+    if (pred_x0 != nullptr) pred_x0[i] = x0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicInc(done, gridDim.x - 1) == gridDim.x - 1) *step = st + 1;
+  }
 }
 
 }  // namespace dfb
@@ -1172,8 +1221,7 @@ int dfb_unet_create(const dfb_unet_cfg* cfg, int device, dfb_handle* out) {
     int rk = kernels_init();
     if (rk) return rk;
   }
-  for (const void* k : {(const void*)step_begin_kernel, (const void*)step_end_kernel,
-                        (const void*)ddim_update_graph_kernel})
+  for (const void* k : {(const void*)step_begin_kernel, (const void*)ddim_update_graph_kernel})
     DFB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
   dfb_unet* e = new dfb_unet();
@@ -1285,34 +1333,93 @@ int dfb_unet_forward(dfb_handle h, const float* x, int x_repeat, const void* t, 
   return run_plan(h, p, s);
 }
 
+constexpr int MAX_SAMPLER_STEPS = 1024;
+
+int dfb_comm_unique_id(void* id128_out) {
+  if (!id128_out) { set_error("null argument"); return DFB_E_INVALID; }
+  NcclApi& n = nccl_api();
+  if (!n.ok) { set_error("libnccl.so.2 could not be loaded"); return DFB_E_STATE; }
+  NcclApi::UniqueId id;
+  const int r = n.GetUniqueId(&id);
+  if (r) { set_error(std::string("ncclGetUniqueId: ") + n.GetErrorString(r)); return DFB_E_CUDA; }
+  memcpy(id128_out, &id, sizeof(id));
+  return 0;
+}
+
+int dfb_comm_init(dfb_handle h, int rank, int world, const void* id128) {
+  if (!h || !id128 || world < 1 || rank < 0 || rank >= world) { set_error("dfb_comm_init: bad argument"); return DFB_E_INVALID; }
+  NcclApi& n = nccl_api();
+  if (!n.ok) { set_error("libnccl.so.2 could not be loaded"); return DFB_E_STATE; }
+  cudaSetDevice(h->device);
+  if (h->comm) { n.CommDestroy(h->comm); h->comm = nullptr; }
+  NcclApi::UniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  const int r = n.CommInitRank(&h->comm, world, id, rank);
+  if (r) { h->comm = nullptr; set_error(std::string("ncclCommInitRank: ") + n.GetErrorString(r)); return DFB_E_CUDA; }
+  h->rank = rank;
+  h->world = world;
+  if (h->smp.exec) { cudaGraphExecDestroy(h->smp.exec); h->smp.exec = nullptr; }
+  return 0;
+}
+
+int dfb_comm_destroy(dfb_handle h) {
+  if (!h) return 0;
+  if (h->comm) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
+  h->rank = 0;
+  h->world = 1;
+  if (h->smp.exec) { cudaGraphExecDestroy(h->smp.exec); h->smp.exec = nullptr; }
+  return 0;
+}
+
 int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* uncond, int n_clips,
                     int ctx_len, float cfg_scale, int S, const int64_t* timesteps,
                     const float* sqrt_one_minus_at, const float* sqrt_at, const float* sqrt_a_prev,
-                    const float* dir_coef, float* pred_x0, void* stream) {
+                    const float* dir_coef, float* pred_x0, float* x_first, float* pred_first, void* stream) {
   if (!h || !x || !cond || !uncond || !timesteps || !sqrt_one_minus_at || !sqrt_at || !sqrt_a_prev ||
       !dir_coef) { set_error("dfb_ddim_sample: null argument"); return DFB_E_INVALID; }
   if (!h->finalized) { set_error("sample before finalize"); return DFB_E_STATE; }
-  const int b_eff = 2 * n_clips;
-  if (n_clips < 1 || b_eff > h->cfg.max_batch || S < 1) {
-    set_error("dfb_ddim_sample: 2*n_clips must be <= max_batch and n_steps >= 1");
+  // (clip, branch) units u = branch * B + clip (the reference's cat([uncond, cond]) order, ddim.py:240-243);
+  // with a communicator, rank r evaluates the contiguous slice [r * 2B / world, (r + 1) * 2B / world)
+  const int units = 2 * n_clips, world = h->comm ? h->world : 1, rank = h->comm ? h->rank : 0;
+  if (n_clips < 1 || units % world || units / world > h->cfg.max_batch || S < 1 || S > MAX_SAMPLER_STEPS ||
+      ctx_len < 1 || ctx_len > h->cfg.max_context_len) {
+    set_error("dfb_ddim_sample: need 1 <= n_steps <= 1024, ctx_len <= max_context_len, and 2*n_clips divisible by the "
+              "world size with 2*n_clips/world <= max_batch");
     return DFB_E_INVALID;
   }
+  const int n_loc = units / world, lo = rank * n_loc;
   cudaStream_t s = (cudaStream_t)stream;
   auto& sm = h->smp;
   const dfb_unet_cfg& c = h->cfg;
-  const size_t n_lat = (size_t)n_clips * c.in_channels * c.latent_h * c.latent_w;
+  const size_t lat = (size_t)c.in_channels * c.latent_h * c.latent_w;
+  const size_t n_lat = (size_t)n_clips * lat;
   const size_t n_ctx = (size_t)n_clips * ctx_len * c.context_dim;
-  const bool rebuild = (sm.n_clips != n_clips || sm.ctx_len != ctx_len || sm.cap_S < S);
-  if (rebuild) {
+  cudaSetDevice(h->device);
+  // ---- engine-owned buffers: allocated once, grown (and the graph dropped) only when a larger call arrives
+  if (sm.coefs == nullptr) {
+    sm.coefs = h->dalloc<float>((size_t)MAX_SAMPLER_STEPS * 5);
+    sm.tsteps = h->dalloc<long long>(MAX_SAMPLER_STEPS);
+    if (sm.step == nullptr) sm.step = h->dalloc<int>(1);
+    sm.done = h->dalloc<unsigned int>(1);
+    sm.t_cur = h->dalloc<long long>(c.max_batch);
+    if (!sm.coefs || !sm.tsteps || !sm.step || !sm.done || !sm.t_cur) return DFB_E_CUDA;
+  }
+  auto grow = [&](float** p, size_t n) -> bool {
+    if (*p) { cudaStreamSynchronize(s); cudaFree(*p); *p = nullptr; }
+    return cudaMalloc(p, n * sizeof(float)) == cudaSuccess;
+  };
+  if (n_lat > sm.cap_lat) {
     if (sm.exec) { cudaGraphExecDestroy(sm.exec); sm.exec = nullptr; }
-    sm.coefs = h->dalloc<float>((size_t)S * 5);
-    sm.tsteps = h->dalloc<long long>(S);
-    if (sm.step == nullptr) sm.step = h->dalloc<int>(1);  // (table-mode plans keep this pointer)
-    sm.t_cur = h->dalloc<long long>(b_eff);
-    sm.eps = h->dalloc<float>(2 * n_lat);
-    sm.ctx_cat = h->dalloc<float>(2 * n_ctx);
-    if (!sm.coefs || !sm.tsteps || !sm.step || !sm.t_cur || !sm.eps || !sm.ctx_cat) return DFB_E_CUDA;
-    sm.n_clips = n_clips; sm.ctx_len = ctx_len; sm.cap_S = S;
+    if (!grow(&sm.eps, 2 * n_lat) || !grow(&sm.x_buf, n_lat) || !grow(&sm.px0_buf, n_lat)) {
+      sm.cap_lat = 0;
+      set_error("dfb_ddim_sample: cudaMalloc failed");
+      return DFB_E_CUDA;
+    }
+    sm.cap_lat = n_lat;
+  }
+  if (2 * n_ctx > sm.cap_ctx) {
+    if (!grow(&sm.ctx_cat, 2 * n_ctx)) { sm.cap_ctx = 0; set_error("dfb_ddim_sample: cudaMalloc failed"); return DFB_E_CUDA; }
+    sm.cap_ctx = 2 * n_ctx;
   }
   std::vector<float> hc((size_t)S * 5);
   std::vector<long long> ht(S);
@@ -1324,11 +1431,14 @@ int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* unco
   DFB_CUDA_OK(cudaMemcpyAsync(sm.coefs, hc.data(), hc.size() * sizeof(float), cudaMemcpyHostToDevice, s));
   DFB_CUDA_OK(cudaMemcpyAsync(sm.tsteps, ht.data(), ht.size() * sizeof(long long), cudaMemcpyHostToDevice, s));
   DFB_CUDA_OK(cudaMemsetAsync(sm.step, 0, sizeof(int), s));
+  DFB_CUDA_OK(cudaMemsetAsync(sm.done, 0, sizeof(unsigned int), s));
+  DFB_CUDA_OK(cudaMemcpyAsync(sm.x_buf, x, n_lat * sizeof(float), cudaMemcpyDeviceToDevice, s));
   // c_in = cat([unconditional_conditioning, c])  (ddim.py:242)
   DFB_CUDA_OK(cudaMemcpyAsync(sm.ctx_cat, uncond, n_ctx * sizeof(float), cudaMemcpyDeviceToDevice, s));
   DFB_CUDA_OK(cudaMemcpyAsync(sm.ctx_cat + n_ctx, cond, n_ctx * sizeof(float), cudaMemcpyDeviceToDevice, s));
   h->last_launches = 0;
-  int r = compute_context(h, sm.ctx_cat, b_eff, ctx_len, s);
+  // cross-attention K/V of this rank's units (step-invariant)
+  int r = compute_context(h, sm.ctx_cat + (size_t)lo * ctx_len * c.context_dim, n_loc, ctx_len, s);
   if (r) return r;
   // ---- per-schedule table of timestep embeddings (see Sampler::emb_tab)
   static const bool no_tab = getenv("DFB_NO_EMB_TABLE") != nullptr;
@@ -1361,19 +1471,40 @@ int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* unco
     }
   }
   Plan* p = nullptr;
-  r = build_plan(h, b_eff, &p, use_tab);
+  r = build_plan(h, n_loc, &p, use_tab);
   if (r) return r;
-  h->cur_x = x; h->cur_x_repeat = 2; h->cur_t = sm.t_cur; h->cur_t_is_float = 0; h->cur_out = sm.eps;
+  h->cur_x = sm.x_buf; h->cur_x_repeat = 1; h->cur_x_nsrc = n_clips; h->cur_x_off = lo;
+  h->cur_t = sm.t_cur; h->cur_t_is_float = 0;
+  h->cur_out = sm.eps + (size_t)lo * lat;   // this rank's slice of the all-units eps tensor (in-place all-gather)
+  const int upd_blocks = (int)std::min<size_t>((n_lat + 1023) / 1024, 64);
+  const int step_extra = (use_tab ? 0 : 1) + (world > 1 ? 1 : 0) + 1;
   auto one_step = [&](cudaStream_t st) -> int {
-    DFB_CUDA_OK(launch_pdl(step_begin_kernel, dim3((b_eff + 127) / 128), dim3(128), 0, st, sm.tsteps, sm.step,
-                           sm.t_cur, b_eff));
+    if (!use_tab)
+      DFB_CUDA_OK(launch_pdl(step_begin_kernel, dim3((n_loc + 127) / 128), dim3(128), 0, st, sm.tsteps, sm.step,
+                             sm.t_cur, n_loc));
     int rr = run_plan(h, p, st);
     if (rr) return rr;
-    DFB_CUDA_OK(launch_pdl(ddim_update_graph_kernel, dim3((unsigned)((n_lat + 255) / 256)), dim3(256), 0, st, x,
-                           sm.eps, n_lat, sm.coefs, sm.step, pred_x0));
-    DFB_CUDA_OK(launch_pdl(step_end_kernel, dim3(1), dim3(1), 0, st, sm.step));
+    if (world > 1) {
+      // the step's only exchange: every rank's eps slice to every rank, captured in the graph
+      const int nr = nccl_api().AllGather(sm.eps + (size_t)lo * lat, sm.eps, (size_t)n_loc * lat, NCCL_FLOAT32,
+                                          h->comm, st);
+      if (nr) { set_error(std::string("ncclAllGather: ") + nccl_api().GetErrorString(nr)); return DFB_E_CUDA; }
+    }
+    DFB_CUDA_OK(launch_pdl(ddim_update_graph_kernel, dim3(upd_blocks), dim3(1024), 0, st, sm.x_buf, sm.eps, n_lat,
+                           sm.coefs, sm.step, sm.done, sm.px0_buf));
     DFB_CUDA_OK(cudaGetLastError());
-    h->last_launches += 3;
+    h->last_launches += step_extra;
+    return 0;
+  };
+  auto log_first = [&]() -> int {   // the reference logs the state after its first step (ddim.py:223-226)
+    if (x_first) DFB_CUDA_OK(cudaMemcpyAsync(x_first, sm.x_buf, n_lat * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (pred_first) DFB_CUDA_OK(cudaMemcpyAsync(pred_first, sm.px0_buf, n_lat * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return 0;
+  };
+  auto finish = [&]() -> int {
+    h->cur_x_nsrc = 0; h->cur_x_off = 0;
+    DFB_CUDA_OK(cudaMemcpyAsync(x, sm.x_buf, n_lat * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (pred_x0) DFB_CUDA_OK(cudaMemcpyAsync(pred_x0, sm.px0_buf, n_lat * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return 0;
   };
   const char* ng = getenv("DFB_NO_GRAPH");
@@ -1381,10 +1512,12 @@ int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* unco
     for (int i = 0; i < S; ++i) {
       r = one_step(s);
       if (r) return r;
+      if (i == 0 && (r = log_first())) return r;
     }
-    return 0;
+    return finish();
   }
-  if (sm.exec == nullptr || sm.x_ptr != x || sm.px0_ptr != pred_x0) {
+  if (sm.exec == nullptr || sm.n_clips != n_clips || sm.ctx_len != ctx_len || sm.table != (int)use_tab ||
+      sm.lo != lo || sm.n_loc != n_loc) {
     if (sm.exec) { cudaGraphExecDestroy(sm.exec); sm.exec = nullptr; }
     // the caller's stream may be the legacy default stream, which cannot capture: record the step
     // on an engine-owned stream, replay the instantiated graph on the caller's stream
@@ -1399,15 +1532,16 @@ int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* unco
     ce = cudaGraphInstantiate(&sm.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) { sm.exec = nullptr; set_error(std::string("graph instantiate failed: ") + cudaGetErrorString(ce)); return DFB_E_CUDA; }
-    sm.x_ptr = x; sm.px0_ptr = pred_x0;
+    sm.n_clips = n_clips; sm.ctx_len = ctx_len; sm.table = (int)use_tab; sm.lo = lo; sm.n_loc = n_loc;
   }
-  const long long per_step = (long long)p->ops.size() + 3;
+  const long long per_step = (long long)p->ops.size() + step_extra;
   h->last_launches = 2;
   for (int i = 0; i < S; ++i) {
     DFB_CUDA_OK(cudaGraphLaunch(sm.exec, s));
     h->last_launches += per_step;
+    if (i == 0 && (r = log_first())) return r;
   }
-  return 0;
+  return finish();
 }
 
 int dfb_unet_profile(dfb_handle h, const float* x, int x_repeat, const void* t, int t_is_float,
@@ -1570,6 +1704,9 @@ int dfb_unet_destroy(dfb_handle h) {
   cudaDeviceSynchronize();
   if (h->smp.exec) cudaGraphExecDestroy(h->smp.exec);
   if (h->smp.cap_stream) cudaStreamDestroy(h->smp.cap_stream);
+  if (h->comm) nccl_api().CommDestroy(h->comm);
+  for (float* q : {h->smp.eps, h->smp.x_buf, h->smp.px0_buf, h->smp.ctx_cat})
+    if (q) cudaFree(q);
   for (auto& kv : h->plans)
     for (void* p : kv.second->owned) cudaFree(p);
   for (void* p : h->owned) cudaFree(p);

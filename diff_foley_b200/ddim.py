@@ -88,26 +88,45 @@ class DDIMSamplerB200(object):
                  img_callback is None and 2 * batch_size <= unet.max_batch)
         lib = L.lib()
         if fused:
-            h = unet.engine(device)
             cond = conditioning.to(device=device, dtype=torch.float32).contiguous()
             unc = unconditional_conditioning.to(device=device, dtype=torch.float32).contiguous()
+            # raw pointers cross the C ABI: every extent the library derives from its config is checked here
+            if (C_, H, W) != (unet.in_channels, *unet.latent_size):
+                raise ValueError(f"shape {tuple(shape)} does not match the UNet latent "
+                                 f"({unet.in_channels}, {unet.latent_size[0]}, {unet.latent_size[1]})")
+            if tuple(img.shape) != (batch_size, C_, H, W):
+                raise ValueError(f"x_T must be [{batch_size},{C_},{H},{W}], got {tuple(img.shape)}")
+            if (cond.dim() != 3 or cond.shape != unc.shape or cond.shape[0] != batch_size or
+                    cond.shape[1] > unet.max_context_len or cond.shape[2] != unet.context_dim):
+                raise ValueError(f"conditioning / unconditional_conditioning must both be [{batch_size}, L <= "
+                                 f"{unet.max_context_len}, {unet.context_dim}], got {tuple(cond.shape)} / {tuple(unc.shape)}")
+            h = unet.engine(device)
+            n_steps = len(st["timesteps"])      # > S when S does not divide 1000 (ddim.py:197-199 runs them all)
             pred = torch.empty_like(img)
+            x1, p1 = torch.empty_like(img), torch.empty_like(img)
             fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
             with torch.cuda.device(device):
                 L.check(lib.dfb_ddim_sample(
                     h, L.ptr(img), L.ptr(cond), L.ptr(unc), batch_size, cond.shape[1],
-                    float(unconditional_guidance_scale), S,
+                    float(unconditional_guidance_scale), n_steps,
                     st["timesteps"].ctypes.data_as(C.POINTER(C.c_int64)), fp(st["sqrt_one_minus_at"]),
-                    fp(st["sqrt_at"]), fp(st["sqrt_a_prev"]), fp(st["dir_coef"]), L.ptr(pred),
+                    fp(st["sqrt_at"]), fp(st["sqrt_a_prev"]), fp(st["dir_coef"]), L.ptr(pred), L.ptr(x1), L.ptr(p1),
                     L.cur_stream()), "dfb_ddim_sample")
-            intermediates["x_inter"].append(img)
+            # the reference logs after the step with index == total_steps - 1 (the first) and after every step
+            # with index % log_every_t == 0 (ddim.py:223-226) -- always the last one (index 0); the fused loop
+            # exposes exactly those two, i.e. the reference's list whenever total_steps <= log_every_t
+            if n_steps > 1:
+                intermediates["x_inter"].append(x1)
+                intermediates["pred_x0"].append(p1)
+            intermediates["x_inter"].append(img.clone())
             intermediates["pred_x0"].append(pred)
             return img, intermediates
         # ---- host loop (ddim.py:204-228) for the call shapes the fused sampler does not take
         n = img.numel()
         pred = torch.empty_like(img)
+        total_steps = len(st["timesteps"])
         for i, step in enumerate(st["timesteps"]):
-            index = S - i - 1
+            index = total_steps - i - 1
             ts = torch.full((batch_size,), int(step), device=device, dtype=torch.long)
             if cfg:
                 e = self.model.apply_model(torch.cat([img] * 2), torch.cat([ts] * 2),
@@ -133,7 +152,7 @@ class DDIMSamplerB200(object):
             img = nxt
             if callback: callback(i)
             if img_callback: img_callback(pred, i)
-            if index % log_every_t == 0 or index == S - 1:
+            if index % log_every_t == 0 or index == total_steps - 1:
                 intermediates["x_inter"].append(img)
                 intermediates["pred_x0"].append(pred.clone())
         return img, intermediates

@@ -27,6 +27,58 @@ def unit_slice(n_clips, world, rank):
     return rank * per, (rank + 1) * per
 
 
+def init_library_comm(unet, group=None):
+    """Creates the library-owned NCCL communicator of `unet`'s engine (SURVEY 8b 'Ownership'): rank 0
+    draws the ncclUniqueId (dfb_comm_unique_id), torch.distributed broadcasts its 128 bytes, every rank
+    calls dfb_comm_init.  Idempotent per (engine, world, rank)."""
+    import ctypes as C
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = next(unet.parameters()).device
+    h = unet.engine(dev)
+    key = (world, rank, h.value)
+    if getattr(unet, "_comm_key", None) == key:
+        return h
+    lib = L.lib()
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        L.check(lib.dfb_comm_unique_id(buf), "dfb_comm_unique_id")
+    t = torch.tensor(list(buf), dtype=torch.uint8)
+    backend = dist.get_backend(group)
+    if backend == "nccl":
+        t = t.to(dev)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ident = (C.c_ubyte * 128)(*t.cpu().tolist())
+    with torch.cuda.device(dev):
+        L.check(lib.dfb_comm_init(h, rank, world, ident), "dfb_comm_init")
+    unet._comm_key = key
+    return h
+
+
+@torch.no_grad()
+def fused_sharded_ddim_sample(ldm, x_T, cond, uncond, scale, num_steps, group=None):
+    """The whole sharded loop as ONE C call per rank (dfb_ddim_sample with a communicator): the per-step
+    graph holds this rank's UNet forward over its units, the NCCL all-gather of eps and the fused update of
+    all B latents; the embedding table and the step counter are the single-GPU sampler's."""
+    import ctypes as C
+    from .ddim import DDIMSamplerB200
+    unet = ldm.model.diffusion_model
+    h = init_library_comm(unet, group)
+    sampler = DDIMSamplerB200(ldm)
+    sampler.make_schedule(num_steps)
+    st = sampler._steps
+    dev = x_T.device
+    x = x_T.detach().to(torch.float32).clone().contiguous()
+    c = cond.detach().to(torch.float32).contiguous()
+    u = uncond.detach().to(torch.float32).contiguous()
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    with torch.cuda.device(dev):
+        L.check(L.lib().dfb_ddim_sample(
+            h, L.ptr(x), L.ptr(c), L.ptr(u), x.shape[0], c.shape[1], float(scale), len(st["timesteps"]),
+            st["timesteps"].ctypes.data_as(C.POINTER(C.c_int64)), fp(st["sqrt_one_minus_at"]), fp(st["sqrt_at"]),
+            fp(st["sqrt_a_prev"]), fp(st["dir_coef"]), None, None, None, L.cur_stream()), "dfb_ddim_sample(sharded)")
+    return x
+
+
 class _EngineUnits:
     """UNet forward of this rank's units as a replayable CUDA graph around dfb_unet_forward."""
 
@@ -78,6 +130,9 @@ def sharded_ddim_sample(ldm, x_T, cond, uncond, scale, num_steps, group=None, ep
     from .ddim import DDIMSamplerB200
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if (eps_fn is None and step_fn is None and world > 1 and x_T.is_cuda and dist.get_backend(group) == "nccl"
+            and 2 * x_T.shape[0] // world <= ldm.model.diffusion_model.max_batch):
+        return fused_sharded_ddim_sample(ldm, x_T, cond, uncond, scale, num_steps, group)
     B = x_T.shape[0]
     lo, hi = unit_slice(B, world, rank)
     dev = x_T.device

@@ -186,6 +186,15 @@ class UNetModelB200(nn.Module):
         self._handle = None
         self._synced = False
         self._device_index = None
+        self._fingerprint = None
+        # a PARENT module's load_state_dict (LatentDiffusion.init_from_ckpt) recurses through
+        # _load_from_state_dict and never calls this module's load_state_dict override: hook the load itself
+        self.register_load_state_dict_post_hook(lambda module, incompatible: setattr(module, "_synced", False))
+
+    def _param_fingerprint(self):
+        """Cheap change detector for in-place edits (p.copy_, optimizer steps): every in-place op bumps the
+        tensor's version counter."""
+        return sum(p._version for p in self.parameters()) + 31 * sum(p.data_ptr() % 9973 for p in self.parameters())
 
     # ------------------------------------------------------------------------------ engine
     def _apply(self, fn, *a, **k):
@@ -227,16 +236,26 @@ class UNetModelB200(nn.Module):
             cfg = self._cfg()
             L.check(lib.dfb_unet_create(C.byref(cfg), idx, C.byref(h)), "dfb_unet_create")
             self._handle, self._device_index, self._synced = h, idx, False
+        if self._synced and self._fingerprint != self._param_fingerprint():
+            self._synced = False
         if not self._synced:
             with torch.cuda.device(idx):
+                # the pack kernels run on the legacy default stream; conversion temporaries are produced on
+                # torch's current stream, which a non-blocking side stream does not order against it
+                side = torch.cuda.current_stream(idx) != torch.cuda.default_stream(idx)
                 for name, p in self.named_parameters():
                     t = p.detach().to(device=dev, dtype=torch.float32).contiguous()
+                    if side:
+                        torch.cuda.current_stream(idx).synchronize()
                     shape = (C.c_int64 * t.dim())(*t.shape)
                     L.check(lib.dfb_unet_set_weight(self._handle, name.encode(), L.ptr(t), shape, t.dim()),
                             f"dfb_unet_set_weight({name})")
+                    if side:
+                        torch.cuda.synchronize(idx)   # `t` may be freed / reused on the side stream next
                 torch.cuda.synchronize(idx)
                 L.check(lib.dfb_unet_finalize(self._handle), "dfb_unet_finalize")
             self._synced = True
+            self._fingerprint = self._param_fingerprint()
         return self._handle
 
     def release(self):

@@ -77,14 +77,28 @@ int dfb_unet_forward(dfb_handle h, const float* x_dev, int x_repeat, const void*
                      int t_is_float, const float* ctx_dev, int ctx_len, float* out_dev, int b_eff,
                      void* stream);
 /* Whole DDIM loop with classifier-free guidance (ddim.py:179-273): x_T -> x_0 in place.
- * cond/uncond: fp32 [B, ctx_len, context_dim]; timesteps: host int64[S] in sampling order
- * (961, 921, ... 1); coefficient arrays are host fp32[S] in the same order:
+ * cond/uncond: fp32 [B, ctx_len, context_dim]; n_steps = the number of entries of the schedule arrays (for
+ * the 'uniform' discretisation that is len(range(0, 1000, 1000 // S)), which exceeds S when S does not
+ * divide 1000 -- the reference runs them all, ddim.py:197-199); timesteps: host int64[n_steps] in sampling
+ * order (961, 921, ... 1); coefficient arrays are host fp32[n_steps] in the same order:
  * sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2).  The step is captured once as a CUDA
- * graph and replayed S times.  pred_x0_dev may be NULL. */
+ * graph over engine-owned staging buffers and replayed n_steps times.  pred_x0_dev may be NULL;
+ * x_first_dev / pred_first_dev (optional) receive x and pred_x0 after the FIRST step, which the
+ * reference's sampler logs into its intermediates (ddim.py:223-226).
+ * With a communicator (dfb_comm_init) the 2B (clip, branch) units are sharded over the ranks: every rank
+ * passes the same (replicated) x / cond / uncond, evaluates its slice of units, and the per-step eps
+ * all-gather (ncclAllGather, captured inside the step graph) is the only exchange. */
 int dfb_ddim_sample(dfb_handle h, float* x_dev, const float* cond_dev, const float* uncond_dev,
                     int n_clips, int ctx_len, float cfg_scale, int n_steps, const int64_t* timesteps,
                     const float* sqrt_one_minus_at, const float* sqrt_at, const float* sqrt_a_prev,
-                    const float* dir_coef, float* pred_x0_dev, void* stream);
+                    const float* dir_coef, float* pred_x0_dev, float* x_first_dev, float* pred_first_dev,
+                    void* stream);
+/* Multi-GPU (one process per GPU): the library owns its NCCL communicator, created from a 128-byte
+ * ncclUniqueId that rank 0 obtains with dfb_comm_unique_id and the host distributes (e.g. a
+ * torch.distributed broadcast); freed by dfb_comm_destroy / dfb_unet_destroy. */
+int dfb_comm_unique_id(void* id128_out);
+int dfb_comm_init(dfb_handle h, int rank, int world, const void* id128);
+int dfb_comm_destroy(dfb_handle h);
 /* Per-launch profile of one UNet forward: runs the plan for b_eff `iters` times with a CUDA event
  * between consecutive launches (on `stream`) and returns, per launch, the kernel kind, its
  * algorithmic FLOPs / bytes and the mean event-timed duration.  Context must have been set. */

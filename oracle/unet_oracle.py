@@ -186,7 +186,7 @@ def seeded_state_dict(cfg, seed=0, dtype=torch.float32):
 def timestep_embedding(t, dim, max_period=10000):
     """util.py:151-171 (repeat_only=False)."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32, device=t.device) / half)
     args = t[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:
