@@ -1351,6 +1351,8 @@ int dfb_comm_init(dfb_handle h, int rank, int world, const void* id128) {
   NcclApi& n = nccl_api();
   if (!n.ok) { set_error("libnccl.so.2 could not be loaded"); return DFB_E_STATE; }
   cudaSetDevice(h->device);
+  // (an instantiated graph that holds an NCCL node keeps the communicator busy: drop the graph first)
+  if (h->smp.exec) { cudaDeviceSynchronize(); cudaGraphExecDestroy(h->smp.exec); h->smp.exec = nullptr; }
   if (h->comm) { n.CommDestroy(h->comm); h->comm = nullptr; }
   NcclApi::UniqueId id;
   memcpy(&id, id128, sizeof(id));
@@ -1358,16 +1360,16 @@ int dfb_comm_init(dfb_handle h, int rank, int world, const void* id128) {
   if (r) { h->comm = nullptr; set_error(std::string("ncclCommInitRank: ") + n.GetErrorString(r)); return DFB_E_CUDA; }
   h->rank = rank;
   h->world = world;
-  if (h->smp.exec) { cudaGraphExecDestroy(h->smp.exec); h->smp.exec = nullptr; }
   return 0;
 }
 
 int dfb_comm_destroy(dfb_handle h) {
   if (!h) return 0;
+  cudaSetDevice(h->device);
+  if (h->smp.exec) { cudaDeviceSynchronize(); cudaGraphExecDestroy(h->smp.exec); h->smp.exec = nullptr; }
   if (h->comm) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
   h->rank = 0;
   h->world = 1;
-  if (h->smp.exec) { cudaGraphExecDestroy(h->smp.exec); h->smp.exec = nullptr; }
   return 0;
 }
 
