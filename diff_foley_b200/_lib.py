@@ -54,6 +54,8 @@ SIGNATURES = {
     "dfb_unet_forward": (_i, [_vp, _fp, _i, _vp, _i, _fp, _i, _fp, _i, _vp]),
     "dfb_ddim_sample": (_i, [_vp, _fp, _fp, _fp, _i, _i, _f, _i, _i64p, C.POINTER(_f), C.POINTER(_f),
                              C.POINTER(_f), C.POINTER(_f), _fp, _fp, _fp, _vp]),
+    "dfb_dpm_solver_sample": (_i, [_vp, _fp, _fp, _fp, _i, _i, _f, _i, C.POINTER(_f), C.POINTER(_f), C.POINTER(_f),
+                                   C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), C.POINTER(C.c_int32), _fp, _vp]),
     "dfb_comm_unique_id": (_i, [_vp]),
     "dfb_comm_init": (_i, [_vp, _i, _i, _vp]),
     "dfb_comm_destroy": (_i, [_vp]),

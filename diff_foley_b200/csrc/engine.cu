@@ -300,6 +300,9 @@ struct dfb_unet {
     float cfg_scale = 0.f;
     float* coefs = nullptr;       // device [MAX_STEPS, 5]
     long long* tsteps = nullptr;  // device [MAX_STEPS]
+    float* tsteps_f = nullptr;    // device [MAX_STEPS]: fractional model-input times (DPM-Solver)
+    float* m_prev = nullptr;      // device [B,4,H,W]: previous data prediction (DPM-Solver++ 2M)
+    int kind = -1;
     int* step = nullptr;          // device scalar
     unsigned int* done = nullptr; // device counter of the update kernel's finished blocks (wraps)
     long long* t_cur = nullptr;   // device [max_batch] (filled per step, non-table mode)
@@ -316,7 +319,7 @@ struct dfb_unet {
     // `*step` (IGemmEpilogue::rowvec_row)
     float* emb_tab = nullptr;            // [EMB_TAB_ROWS, emb_all.N]
     __half *emb_a = nullptr, *emb_b = nullptr;
-    std::vector<long long> tab_steps;    // schedule the table was built for
+    std::vector<double> tab_steps;       // schedule the table was built for
     long long tab_epoch = -1;
   } smp;
   long long weights_epoch = 0;  // bumped by set_weight / finalize
@@ -1162,6 +1165,7 @@ __global__ void step_begin_kernel(const long long* __restrict__ tsteps, const in
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) t_cur[i] = tsteps[*step];
 }
+constexpr int SAMPLER_COEFS = 8;  // floats per step in the device coefficient table
 // coefs[step] = {sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), cfg_scale}.  The last block to
 // finish advances the step counter (every block read it before its arrival on `done`, a counter that wraps
 // at gridDim.x): no separate counter kernel.
@@ -1172,7 +1176,7 @@ __global__ void ddim_update_graph_kernel(float* __restrict__ x, const float* __r
   pdl_wait();
   pdl_launch_dependents();
   const int st = *step;
-  const float* c = coefs + 5 * st;
+  const float* c = coefs + SAMPLER_COEFS * st;
   const float c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4];
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float eu = eps[i], ec = eps[n + i];
@@ -1180,6 +1184,41 @@ __global__ void ddim_update_graph_kernel(float* __restrict__ x, const float* __r
     const float x0 = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(c0, e)), c1);
     x[i] = __fadd_rn(__fmul_rn(c2, x0), __fmul_rn(c3, e));
     if (pred_x0 != nullptr) pred_x0[i] = x0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicInc(done, gridDim.x - 1) == gridDim.x - 1) *step = st + 1;
+  }
+}
+
+// DPM-Solver++(2M) update (dpm_solver.py:386-394 data prediction, :504-533 first-order, :755-790 second-order
+// multistep, 'dpm_solver' type) fused with the classifier-free-guidance combine (:340-344).  Per step k the
+// host precomputes coefs[k] = {sigma_k, alpha_k, sigma_{k+1}/sigma_k, alpha_{k+1}(e^{-h}-1), 1/r0, order, cfg}:
+//   m_k = (x - sigma_k e) / alpha_k;   order 1: x <- cx x - A m_k;   order 2: x <- cx x - A m_k - 0.5 A D1,
+//   D1 = (1/r0)(m_k - m_{k-1}).   The reference's fp32 operation order, no FMA contraction.
+__global__ void dpm2m_update_graph_kernel(float* __restrict__ x, const float* __restrict__ eps, size_t n,
+                                          const float* __restrict__ coefs, int* __restrict__ step,
+                                          unsigned int* __restrict__ done, float* __restrict__ m_prev,
+                                          float* __restrict__ pred_x0) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int st = *step;
+  const float* c = coefs + SAMPLER_COEFS * st;
+  const float sig = c[0], alp = c[1], cx = c[2], A = c[3], inv_r0 = c[4], order = c[5], cfg = c[6];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float eu = eps[i], ec = eps[n + i];
+    const float e = __fadd_rn(eu, __fmul_rn(cfg, __fsub_rn(ec, eu)));
+    const float xi = x[i];
+    const float m = __fdiv_rn(__fsub_rn(xi, __fmul_rn(sig, e)), alp);
+    float xn = __fsub_rn(__fmul_rn(cx, xi), __fmul_rn(A, m));
+    if (order > 1.5f) {
+      const float d1 = __fmul_rn(inv_r0, __fsub_rn(m, m_prev[i]));
+      xn = __fsub_rn(xn, __fmul_rn(__fmul_rn(0.5f, A), d1));
+    }
+    x[i] = xn;
+    m_prev[i] = m;
+    if (pred_x0 != nullptr) pred_x0[i] = m;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -1221,7 +1260,8 @@ int dfb_unet_create(const dfb_unet_cfg* cfg, int device, dfb_handle* out) {
     int rk = kernels_init();
     if (rk) return rk;
   }
-  for (const void* k : {(const void*)step_begin_kernel, (const void*)ddim_update_graph_kernel})
+  for (const void* k : {(const void*)step_begin_kernel, (const void*)ddim_update_graph_kernel,
+                        (const void*)dpm2m_update_graph_kernel})
     DFB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
   dfb_unet* e = new dfb_unet();
@@ -1373,12 +1413,13 @@ int dfb_comm_destroy(dfb_handle h) {
   return 0;
 }
 
-int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* uncond, int n_clips,
-                    int ctx_len, float cfg_scale, int S, const int64_t* timesteps,
-                    const float* sqrt_one_minus_at, const float* sqrt_at, const float* sqrt_a_prev,
-                    const float* dir_coef, float* pred_x0, float* x_first, float* pred_first, void* stream) {
-  if (!h || !x || !cond || !uncond || !timesteps || !sqrt_one_minus_at || !sqrt_at || !sqrt_a_prev ||
-      !dir_coef) { set_error("dfb_ddim_sample: null argument"); return DFB_E_INVALID; }
+enum { SAMPLER_DDIM = 0, SAMPLER_DPM2M = 1 };
+
+// One fused sampling loop: kind selects the update kernel; t_int (DDIM: discrete timesteps) or t_flt (DPM-Solver:
+// fractional model-input times) in sampling order, hc = host coefficient rows [S][SAMPLER_COEFS].
+static int sample_core(dfb_handle h, int kind, float* x, const float* cond, const float* uncond, int n_clips,
+                       int ctx_len, int S, const int64_t* t_int, const float* t_flt, const std::vector<float>& hc,
+                       float* pred_x0, float* x_first, float* pred_first, void* stream) {
   if (!h->finalized) { set_error("sample before finalize"); return DFB_E_STATE; }
   // (clip, branch) units u = branch * B + clip (the reference's cat([uncond, cond]) order, ddim.py:240-243);
   // with a communicator, rank r evaluates the contiguous slice [r * 2B / world, (r + 1) * 2B / world)
@@ -1399,8 +1440,9 @@ int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* unco
   cudaSetDevice(h->device);
   // ---- engine-owned buffers: allocated once, grown (and the graph dropped) only when a larger call arrives
   if (sm.coefs == nullptr) {
-    sm.coefs = h->dalloc<float>((size_t)MAX_SAMPLER_STEPS * 5);
+    sm.coefs = h->dalloc<float>((size_t)MAX_SAMPLER_STEPS * SAMPLER_COEFS);
     sm.tsteps = h->dalloc<long long>(MAX_SAMPLER_STEPS);
+    sm.tsteps_f = h->dalloc<float>(MAX_SAMPLER_STEPS);
     if (sm.step == nullptr) sm.step = h->dalloc<int>(1);
     sm.done = h->dalloc<unsigned int>(1);
     sm.t_cur = h->dalloc<long long>(c.max_batch);
@@ -1412,7 +1454,7 @@ int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* unco
   };
   if (n_lat > sm.cap_lat) {
     if (sm.exec) { cudaGraphExecDestroy(sm.exec); sm.exec = nullptr; }
-    if (!grow(&sm.eps, 2 * n_lat) || !grow(&sm.x_buf, n_lat) || !grow(&sm.px0_buf, n_lat)) {
+    if (!grow(&sm.eps, 2 * n_lat) || !grow(&sm.x_buf, n_lat) || !grow(&sm.px0_buf, n_lat) || !grow(&sm.m_prev, n_lat)) {
       sm.cap_lat = 0;
       set_error("dfb_ddim_sample: cudaMalloc failed");
       return DFB_E_CUDA;
@@ -1423,15 +1465,17 @@ int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* unco
     if (!grow(&sm.ctx_cat, 2 * n_ctx)) { sm.cap_ctx = 0; set_error("dfb_ddim_sample: cudaMalloc failed"); return DFB_E_CUDA; }
     sm.cap_ctx = 2 * n_ctx;
   }
-  std::vector<float> hc((size_t)S * 5);
-  std::vector<long long> ht(S);
+  std::vector<long long> ht(S, 0);
+  std::vector<float> hf(S, 0.f);
+  std::vector<double> hkey(S);
   for (int i = 0; i < S; ++i) {
-    hc[5 * i + 0] = sqrt_one_minus_at[i]; hc[5 * i + 1] = sqrt_at[i]; hc[5 * i + 2] = sqrt_a_prev[i];
-    hc[5 * i + 3] = dir_coef[i]; hc[5 * i + 4] = cfg_scale;
-    ht[i] = (long long)timesteps[i];
+    if (t_int) ht[i] = (long long)t_int[i];
+    if (t_flt) hf[i] = t_flt[i];
+    hkey[i] = t_int ? (double)t_int[i] : (double)t_flt[i] + 1e9;   // (int and float schedules never collide)
   }
   DFB_CUDA_OK(cudaMemcpyAsync(sm.coefs, hc.data(), hc.size() * sizeof(float), cudaMemcpyHostToDevice, s));
   DFB_CUDA_OK(cudaMemcpyAsync(sm.tsteps, ht.data(), ht.size() * sizeof(long long), cudaMemcpyHostToDevice, s));
+  DFB_CUDA_OK(cudaMemcpyAsync(sm.tsteps_f, hf.data(), hf.size() * sizeof(float), cudaMemcpyHostToDevice, s));
   DFB_CUDA_OK(cudaMemsetAsync(sm.step, 0, sizeof(int), s));
   DFB_CUDA_OK(cudaMemsetAsync(sm.done, 0, sizeof(unsigned int), s));
   DFB_CUDA_OK(cudaMemcpyAsync(sm.x_buf, x, n_lat * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -1444,7 +1488,11 @@ int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* unco
   if (r) return r;
   // ---- per-schedule table of timestep embeddings (see Sampler::emb_tab)
   static const bool no_tab = getenv("DFB_NO_EMB_TABLE") != nullptr;
-  const bool use_tab = !no_tab && S <= EMB_TAB_ROWS;
+  const bool use_tab = (!no_tab || t_flt != nullptr) && S <= EMB_TAB_ROWS;
+  if (t_flt != nullptr && !use_tab) {
+    set_error("fractional-time samplers serve the timestep embeddings from the per-schedule table: n_steps <= 256");
+    return DFB_E_INVALID;
+  }
   if (use_tab) {
     const int mc = c.model_channels, td = h->time_dim;
     if (sm.emb_tab == nullptr) {
@@ -1453,8 +1501,8 @@ int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* unco
       sm.emb_b = h->dalloc<__half>((size_t)EMB_TAB_ROWS * td);
       if (!sm.emb_tab || !sm.emb_a || !sm.emb_b) return DFB_E_CUDA;
     }
-    if (sm.tab_epoch != h->weights_epoch || sm.tab_steps != ht) {
-      r = temb_launch(sm.tsteps, 0, S, mc, sm.emb_a, s);
+    if (sm.tab_epoch != h->weights_epoch || sm.tab_steps != hkey) {
+      r = t_flt ? temb_launch(sm.tsteps_f, 1, S, mc, sm.emb_a, s) : temb_launch(sm.tsteps, 0, S, mc, sm.emb_a, s);
       const struct { const __half* a; const Lin* lin; int K; IGemmEpilogue ep; } chain[3] = {
           {sm.emb_a, &h->time1, mc, Builder::ep_f16(sm.emb_b, td, ACT_SILU)},
           {sm.emb_b, &h->time2, td, Builder::ep_f16(sm.emb_a, td, ACT_SILU)},
@@ -1467,7 +1515,7 @@ int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* unco
         if (!r) r = igemm_launch(ip, s);
       }
       if (r) return r;
-      sm.tab_steps = ht;
+      sm.tab_steps = hkey;
       sm.tab_epoch = h->weights_epoch;
       h->last_launches += 4;
     }
@@ -1492,8 +1540,12 @@ int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* unco
                                           h->comm, st);
       if (nr) { set_error(std::string("ncclAllGather: ") + nccl_api().GetErrorString(nr)); return DFB_E_CUDA; }
     }
-    DFB_CUDA_OK(launch_pdl(ddim_update_graph_kernel, dim3(upd_blocks), dim3(1024), 0, st, sm.x_buf, sm.eps, n_lat,
-                           sm.coefs, sm.step, sm.done, sm.px0_buf));
+    if (kind == SAMPLER_DDIM)
+      DFB_CUDA_OK(launch_pdl(ddim_update_graph_kernel, dim3(upd_blocks), dim3(1024), 0, st, sm.x_buf, sm.eps, n_lat,
+                             sm.coefs, sm.step, sm.done, sm.px0_buf));
+    else
+      DFB_CUDA_OK(launch_pdl(dpm2m_update_graph_kernel, dim3(upd_blocks), dim3(1024), 0, st, sm.x_buf, sm.eps, n_lat,
+                             sm.coefs, sm.step, sm.done, sm.m_prev, sm.px0_buf));
     DFB_CUDA_OK(cudaGetLastError());
     h->last_launches += step_extra;
     return 0;
@@ -1519,7 +1571,7 @@ int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* unco
     return finish();
   }
   if (sm.exec == nullptr || sm.n_clips != n_clips || sm.ctx_len != ctx_len || sm.table != (int)use_tab ||
-      sm.lo != lo || sm.n_loc != n_loc) {
+      sm.lo != lo || sm.n_loc != n_loc || sm.kind != kind) {
     if (sm.exec) { cudaGraphExecDestroy(sm.exec); sm.exec = nullptr; }
     // the caller's stream may be the legacy default stream, which cannot capture: record the step
     // on an engine-owned stream, replay the instantiated graph on the caller's stream
@@ -1534,7 +1586,7 @@ int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* unco
     ce = cudaGraphInstantiate(&sm.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) { sm.exec = nullptr; set_error(std::string("graph instantiate failed: ") + cudaGetErrorString(ce)); return DFB_E_CUDA; }
-    sm.n_clips = n_clips; sm.ctx_len = ctx_len; sm.table = (int)use_tab; sm.lo = lo; sm.n_loc = n_loc;
+    sm.n_clips = n_clips; sm.ctx_len = ctx_len; sm.table = (int)use_tab; sm.lo = lo; sm.n_loc = n_loc; sm.kind = kind;
   }
   const long long per_step = (long long)p->ops.size() + step_extra;
   h->last_launches = 2;
@@ -1544,6 +1596,42 @@ int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* unco
     if (i == 0 && (r = log_first())) return r;
   }
   return finish();
+}
+
+int dfb_ddim_sample(dfb_handle h, float* x, const float* cond, const float* uncond, int n_clips,
+                    int ctx_len, float cfg_scale, int S, const int64_t* timesteps,
+                    const float* sqrt_one_minus_at, const float* sqrt_at, const float* sqrt_a_prev,
+                    const float* dir_coef, float* pred_x0, float* x_first, float* pred_first, void* stream) {
+  if (!h || !x || !cond || !uncond || !timesteps || !sqrt_one_minus_at || !sqrt_at || !sqrt_a_prev ||
+      !dir_coef) { set_error("dfb_ddim_sample: null argument"); return DFB_E_INVALID; }
+  if (S < 1 || S > MAX_SAMPLER_STEPS) { set_error("dfb_ddim_sample: need 1 <= n_steps <= 1024"); return DFB_E_INVALID; }
+  std::vector<float> hc((size_t)S * SAMPLER_COEFS, 0.f);
+  for (int i = 0; i < S; ++i) {
+    float* c = &hc[(size_t)SAMPLER_COEFS * i];
+    c[0] = sqrt_one_minus_at[i]; c[1] = sqrt_at[i]; c[2] = sqrt_a_prev[i]; c[3] = dir_coef[i]; c[4] = cfg_scale;
+  }
+  return sample_core(h, SAMPLER_DDIM, x, cond, uncond, n_clips, ctx_len, S, timesteps, nullptr, hc, pred_x0,
+                     x_first, pred_first, stream);
+}
+
+int dfb_dpm_solver_sample(dfb_handle h, float* x, const float* cond, const float* uncond, int n_clips,
+                          int ctx_len, float cfg_scale, int n_evals, const float* t_input, const float* sigma,
+                          const float* alpha, const float* cx, const float* a_coef, const float* inv_r0,
+                          const int32_t* order, float* pred_x0, void* stream) {
+  if (!h || !x || !cond || !uncond || !t_input || !sigma || !alpha || !cx || !a_coef || !inv_r0 || !order) {
+    set_error("dfb_dpm_solver_sample: null argument");
+    return DFB_E_INVALID;
+  }
+  if (n_evals < 1 || n_evals > MAX_SAMPLER_STEPS) { set_error("dfb_dpm_solver_sample: need 1 <= n_evals <= 1024"); return DFB_E_INVALID; }
+  std::vector<float> hc((size_t)n_evals * SAMPLER_COEFS, 0.f);
+  for (int i = 0; i < n_evals; ++i) {
+    float* c = &hc[(size_t)SAMPLER_COEFS * i];
+    if (order[i] != 1 && order[i] != 2) { set_error("dfb_dpm_solver_sample: step order must be 1 or 2"); return DFB_E_INVALID; }
+    c[0] = sigma[i]; c[1] = alpha[i]; c[2] = cx[i]; c[3] = a_coef[i]; c[4] = inv_r0[i]; c[5] = (float)order[i];
+    c[6] = cfg_scale;
+  }
+  return sample_core(h, SAMPLER_DPM2M, x, cond, uncond, n_clips, ctx_len, n_evals, nullptr, t_input, hc, pred_x0,
+                     nullptr, nullptr, stream);
 }
 
 int dfb_unet_profile(dfb_handle h, const float* x, int x_repeat, const void* t, int t_is_float,
@@ -1707,7 +1795,7 @@ int dfb_unet_destroy(dfb_handle h) {
   if (h->smp.exec) cudaGraphExecDestroy(h->smp.exec);
   if (h->smp.cap_stream) cudaStreamDestroy(h->smp.cap_stream);
   if (h->comm) nccl_api().CommDestroy(h->comm);
-  for (float* q : {h->smp.eps, h->smp.x_buf, h->smp.px0_buf, h->smp.ctx_cat})
+  for (float* q : {h->smp.eps, h->smp.x_buf, h->smp.px0_buf, h->smp.m_prev, h->smp.ctx_cat})
     if (q) cudaFree(q);
   for (auto& kv : h->plans)
     for (void* p : kv.second->owned) cudaFree(p);

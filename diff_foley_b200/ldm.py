@@ -109,21 +109,37 @@ class LatentDiffusionB200(nn.Module):
     @torch.no_grad()
     def sample_log_diff_sampler(self, cond, batch_size, sampler_name, ddim_steps, size_len=64,
                                 unconditional_guidance_scale=1.0, unconditional_conditioning=None, **kwargs):
-        if sampler_name != "DDIM":
-            raise NotImplementedError("the B200 hot path implements the DDIM sampler (BASELINE north star)")
         shape = (self.channels, 16, size_len)                # ddpm.py:1293
-        return DDIMSamplerB200(self).sample(ddim_steps, batch_size, shape, cond, verbose=False,
-                                            unconditional_guidance_scale=unconditional_guidance_scale,
-                                            unconditional_conditioning=unconditional_conditioning, **kwargs)
+        if sampler_name == "DDIM":
+            sampler = DDIMSamplerB200(self)
+        elif sampler_name == "DPM_Solver":                   # ddpm.py:1297-1301 (the notebook's default)
+            from .dpm_solver import DPMSolverSamplerB200
+            sampler = DPMSolverSamplerB200(self)
+        elif sampler_name == "PLMS":                         # ddpm.py:1303-1307
+            from .plms import PLMSSamplerB200
+            sampler = PLMSSamplerB200(self)
+        else:
+            raise NotImplementedError(f"sampler_name {sampler_name!r}: DDIM, DPM_Solver and PLMS are implemented "
+                                      "(the reference's fall-through is its ancestral DDPM loop, outside the hot path)")
+        return sampler.sample(ddim_steps, batch_size, shape, cond, verbose=False,
+                              unconditional_guidance_scale=unconditional_guidance_scale,
+                              unconditional_conditioning=unconditional_conditioning, **kwargs)
 
     @torch.no_grad()
     def sample_log_with_classifier_diff_sampler(self, embed_cond, origin_cond, batch_size, sampler_name="DDIM",
                                                 ddim_steps=250, size_len=64, unconditional_guidance_scale=1.0,
                                                 unconditional_conditioning=None, classifier=None,
                                                 classifier_guide_scale=0.0, **kwargs):
-        if sampler_name != "DDIM":
-            raise NotImplementedError("the B200 hot path implements the DDIM sampler (BASELINE north star)")
         shape = (self.channels, 16, size_len)                # ddpm.py:1341
+        if sampler_name == "DPM_Solver":                     # ddpm.py:1346-1350
+            from .dpm_solver import DPMSolverSamplerB200
+            return DPMSolverSamplerB200(self).sample_with_classifier(
+                ddim_steps, batch_size, shape, embed_cond, origin_cond=origin_cond,
+                unconditional_guidance_scale=unconditional_guidance_scale,
+                unconditional_conditioning=unconditional_conditioning, classifier=classifier,
+                classifier_guide_scale=classifier_guide_scale, **kwargs)
+        if sampler_name != "DDIM":
+            raise NotImplementedError(f"sampler_name {sampler_name!r}: DDIM and DPM_Solver take classifier guidance")
         return DDIMSamplerB200(self).sample_with_classifier(
             ddim_steps, batch_size, shape, embed_cond, origin_cond=origin_cond, verbose=False,
             unconditional_guidance_scale=unconditional_guidance_scale,

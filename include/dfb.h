@@ -93,6 +93,17 @@ int dfb_ddim_sample(dfb_handle h, float* x_dev, const float* cond_dev, const flo
                     const float* sqrt_one_minus_at, const float* sqrt_at, const float* sqrt_a_prev,
                     const float* dir_coef, float* pred_x0_dev, float* x_first_dev, float* pred_first_dev,
                     void* stream);
+/* DPM-Solver++(2M) -- the reference's default sampler in the notebook (dpm_solver/sampler.py:89-156:
+ * predict_x0, multistep order 2, 'time_uniform', lower_order_final) -- with classifier-free guidance, same
+ * fused step graph as dfb_ddim_sample.  Host arrays of n_evals entries, one per model evaluation k (at the
+ * continuous time t_k): t_input[k] = fractional model-input time (t_k - 1/N) * 1000 (dpm_solver.py:278-287),
+ * sigma[k], alpha[k] = marginal std / mean coefficient at t_k (data prediction, :386-394), cx[k] =
+ * sigma_{k+1}/sigma_k, a_coef[k] = alpha_{k+1} (e^{-h} - 1), inv_r0[k] = h / h_0, order[k] in {1, 2}
+ * (:504-533, :755-790).  n_evals <= 256.  x: x_T -> x_0 in place; pred_x0_dev (optional) = last data prediction. */
+int dfb_dpm_solver_sample(dfb_handle h, float* x_dev, const float* cond_dev, const float* uncond_dev,
+                          int n_clips, int ctx_len, float cfg_scale, int n_evals, const float* t_input,
+                          const float* sigma, const float* alpha, const float* cx, const float* a_coef,
+                          const float* inv_r0, const int32_t* order, float* pred_x0_dev, void* stream);
 /* Multi-GPU (one process per GPU): the library owns its NCCL communicator, created from a 128-byte
  * ncclUniqueId that rank 0 obtains with dfb_comm_unique_id and the host distributes (e.g. a
  * torch.distributed broadcast); freed by dfb_comm_destroy / dfb_unet_destroy. */

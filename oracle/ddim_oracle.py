@@ -94,3 +94,12 @@ def cond_stage(sd, feats):
     learned positional embedding of the first seq_len rows."""
     x = F.linear(feats, sd["embedder.0.weight"], sd["embedder.0.bias"])
     return x + sd["pos_emb.weight"][: feats.shape[1]][None]
+
+
+def cond_stage_seeded_state(seed, origin_dim=512, embed_dim=768, seq_len=40):
+    """Seeded parameters of the cond-stage embedder under the reference's keys (regenerated identically by the
+    golden generator and by the tests, so the 1.6 MB of weights never enter a fixture)."""
+    g = torch.Generator().manual_seed(seed)
+    shapes = {"embedder.0.weight": (embed_dim, origin_dim), "embedder.0.bias": (embed_dim,),
+              "pos_emb.weight": (seq_len, embed_dim)}
+    return {k: torch.randn(v, generator=g) * (0.05 if len(v) > 1 else 0.1) for k, v in shapes.items()}

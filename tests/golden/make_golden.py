@@ -4,6 +4,8 @@ weights (oracle.unet_oracle.seeded_state_dict).  Run in the build container only
 
     python tests/golden/make_golden.py            # all fixtures  (~4 min on 8 vCPU)
     python tests/golden/make_golden.py small      # just the reduced-width ones
+    python tests/golden/make_golden.py r2         # the round-2 additions (cond embed, DPM-Solver, PLMS, S=30,
+                                                  # full-width classifier-guided DDIM)
 
 The reference ships no tests or golden vectors of its own, so these files are what pins
 the oracle (oracle/) and, through it and directly, the CUDA path.  Nothing here is read at run time
@@ -201,6 +203,50 @@ def gen_ddim_classifier(name, ucfg, ccfg, seed, n_clips, steps, scale, cscale):
     print(f"{name}: latent rms {float(samples.pow(2).mean().sqrt()):.4f} ({time.time() - t0:.1f}s)")
 
 
+def gen_sampler(name, kind, cfg, seed, n_clips, steps, scale):
+    """The reference's DPMSolverSampler.sample (dpm_solver/sampler.py:25-87: DPM-Solver++ multistep order 2,
+    the notebook's default) or PLMSSampler.sample (plms.py:57-112) on CPU, CFG `scale`."""
+    t0 = time.time()
+    if kind == "dpm":
+        from diff_foley.models.diffusion.dpm_solver import DPMSolverSampler as Ref
+    else:
+        from diff_foley.models.diffusion.plms import PLMSSampler as Ref
+
+    class Cpu(Ref):  # register_buffer hard-codes .to("cuda") (sampler.py:18-22, plms.py:17-21)
+        def register_buffer(self, name, attr):
+            setattr(self, name, attr)
+
+    unet = ref_unet(cfg)
+    unet.load_state_dict(unet_oracle.seeded_state_dict(cfg, seed), strict=True)
+    g = torch.Generator().manual_seed(seed + 4000)
+    x_T = torch.randn(n_clips, cfg["in_channels"], cfg["latent_h"], cfg["latent_w"], generator=g)
+    cond = torch.randn(n_clips, cfg["context_len"], cfg["context_dim"], generator=g)
+    sampler = Cpu(_StubLDM(unet))
+    with torch.no_grad():
+        samples, _ = sampler.sample(S=steps, batch_size=n_clips,
+                                    shape=(cfg["in_channels"], cfg["latent_h"], cfg["latent_w"]), conditioning=cond,
+                                    eta=0.0, verbose=False, x_T=x_T.clone(), unconditional_guidance_scale=scale,
+                                    unconditional_conditioning=torch.zeros_like(cond))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), x_T=x_T.numpy(), cond=cond.numpy(), samples=samples.numpy(),
+                        seed=np.int64(seed), steps=np.int64(steps), scale=np.float32(scale))
+    print(f"{name}: latent rms {float(samples.pow(2).mean().sqrt()):.4f} ({time.time() - t0:.1f}s)")
+
+
+def gen_cond_embed(name="cond_embed", seed=41):
+    """Video_Feat_Encoder_Posembed.forward (cond_stage/video_feat_encoder.py:4-18) with the Stage2_LDM.yaml
+    parameters (origin_dim 512, embed_dim 768, seq_len 40) on seeded weights and unit-norm CAVP-like features."""
+    from diff_foley.modules.cond_stage.video_feat_encoder import Video_Feat_Encoder_Posembed
+    m = Video_Feat_Encoder_Posembed(origin_dim=512, embed_dim=768, seq_len=40).eval()
+    sd = ddim_oracle.cond_stage_seeded_state(seed)
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed + 1)
+    feats = torch.nn.functional.normalize(torch.randn(3, 32, 512, generator=g), dim=-1)
+    with torch.no_grad():
+        out = m(feats)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), feats=feats.numpy(), out=out.numpy(), seed=np.int64(seed))
+    print(f"{name}: out {tuple(out.shape)} rms {float(out.pow(2).mean().sqrt()):.4f}")
+
+
 SMALL = unet_oracle.small_unet_cfg()                       # 64 ch, heads 4 -> head dims 16/32/64
 SMALL_ODD = unet_oracle.small_unet_cfg(model_channels=128, channel_mult=(1, 2), num_heads=8,
                                        context_dim=64, latent_h=8, latent_w=16, context_len=33,
@@ -212,16 +258,25 @@ if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     taps = ("input_blocks.1", "input_blocks.3", "input_blocks.4", "middle_block", "output_blocks.2",
             "output_blocks.5", "output_blocks.11")
-    gen_unet("unet_small", SMALL, 1, 2, [961, 961], taps)
-    gen_unet("unet_small_b3", SMALL, 2, 3, [41, 500, 999])
-    gen_unet("unet_small_odd", SMALL_ODD, 3, 2, [1, 1], ("input_blocks.1", "middle_block"))
-    gen_ddim("ddim_small", SMALL, 1, 2, 25, 4.5)
-    gen_ddim("ddim_small_ldm", SMALL, 4, 1, 5, 4.5, use_real_ldm=True)
     from oracle import classifier_oracle
     CLF_SMALL = dict(classifier_oracle.DIFF_FOLEY_CLASSIFIER, model_channels=64, num_heads=4, context_dim=64)
-    gen_classifier("classifier_small", CLF_SMALL, 5, 3, 33)
-    gen_classifier("classifier_full", classifier_oracle.DIFF_FOLEY_CLASSIFIER, 6, 2, 33)
-    gen_ddim_classifier("ddim_classifier_small", SMALL, CLF_SMALL, 9, 2, 25, 4.5, 50.0)
+    if which in ("all", "small"):
+        gen_unet("unet_small", SMALL, 1, 2, [961, 961], taps)
+        gen_unet("unet_small_b3", SMALL, 2, 3, [41, 500, 999])
+        gen_unet("unet_small_odd", SMALL_ODD, 3, 2, [1, 1], ("input_blocks.1", "middle_block"))
+        gen_ddim("ddim_small", SMALL, 1, 2, 25, 4.5)
+        gen_ddim("ddim_small_ldm", SMALL, 4, 1, 5, 4.5, use_real_ldm=True)
+        gen_classifier("classifier_small", CLF_SMALL, 5, 3, 33)
+        gen_classifier("classifier_full", classifier_oracle.DIFF_FOLEY_CLASSIFIER, 6, 2, 33)
+        gen_ddim_classifier("ddim_classifier_small", SMALL, CLF_SMALL, 9, 2, 25, 4.5, 50.0)
+    if which in ("all", "r2"):
+        gen_cond_embed()
+        gen_ddim("ddim_small_s30", SMALL, 11, 1, 30, 4.5)      # 1000 % 30 != 0: 34 schedule entries, all run
+        gen_sampler("dpm_small", "dpm", SMALL, 12, 2, 25, 4.5)
+        gen_sampler("dpm_small_s10", "dpm", SMALL, 13, 1, 10, 4.5)   # steps < 15: lower-order final step
+        gen_sampler("plms_small", "plms", SMALL, 14, 2, 25, 4.5)
+        # config 3 at FULL width: CFG 4.5 + classifier guidance 50, 5 steps (1, 201, ..., 801)
+        gen_ddim_classifier("ddim_classifier_full", FULL, classifier_oracle.DIFF_FOLEY_CLASSIFIER, 15, 1, 5, 4.5, 50.0)
     if which == "all":
         gen_unet("unet_full", FULL, 7, 2, [961, 961])
         gen_unet("unet_full_t41", FULL, 7, 2, [41, 41])

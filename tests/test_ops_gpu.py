@@ -184,13 +184,24 @@ def test_conv3x3(B, H, W, C, N, splits):
     assert rel_l2(out, ref) < 3e-6
 
 
-@pytest.mark.parametrize("C0,C1,HW,eps,silu", [
-    (320, 0, 1024, 1e-5, 1), (640, 320, 1024, 1e-5, 1), (1280, 640, 256, 1e-5, 1),
-    (1280, 1280, 16, 1e-5, 1), (1280, 0, 64, 1e-6, 0), (640, 0, 256, 1e-6, 0), (128, 0, 1024, 1e-5, 1),
-])
-def test_groupnorm(C0, C1, HW, eps, silu):
+# every (C, HW) GroupNorm call site of one UNet forward (SURVEY 8a'), with the source split the plan uses (the
+# skip concat is read from two tensors), both eps (ResBlock 1e-5 + SiLU / SpatialTransformer.norm 1e-6, no
+# SiLU), at B_eff = 2 and -- for the shapes whose launch geometry changes -- B_eff = 16
+GN_SITES = [
+    (320, 0, 1024, 1e-5, 1), (320, 0, 1024, 1e-6, 0), (320, 320, 1024, 1e-5, 1), (640, 320, 1024, 1e-5, 1),
+    (320, 0, 256, 1e-5, 1), (640, 0, 256, 1e-5, 1), (640, 0, 256, 1e-6, 0), (640, 320, 256, 1e-5, 1),
+    (640, 640, 256, 1e-5, 1), (1280, 640, 256, 1e-5, 1), (640, 0, 64, 1e-5, 1), (1280, 0, 64, 1e-5, 1),
+    (1280, 0, 64, 1e-6, 0), (1280, 640, 64, 1e-5, 1), (1280, 1280, 64, 1e-5, 1), (1280, 0, 16, 1e-5, 1),
+    (1280, 0, 16, 1e-6, 0), (1280, 1280, 16, 1e-5, 1), (128, 0, 1024, 1e-5, 1),
+]
+
+
+@pytest.mark.parametrize("B", [2, 16])
+@pytest.mark.parametrize("C0,C1,HW,eps,silu", GN_SITES)
+def test_groupnorm(C0, C1, HW, eps, silu, B):
+    if B == 16 and (C0 + C1, HW) not in ((320, 1024), (960, 1024), (640, 256), (1920, 256), (1280, 64), (2560, 16)):
+        pytest.skip("B_eff = 16 is exercised on one shape per level / source split")
     g = torch.Generator(device="cpu").manual_seed(C0 + C1 + HW)
-    B = 2
     x0 = (torch.randn(B, HW, C0, generator=g) * 2 + 0.5).to(DEV)
     x1 = (torch.randn(B, HW, C1, generator=g) * 3 - 1).to(DEV) if C1 else None
     C = C0 + C1

@@ -176,3 +176,94 @@ def test_cavp_module_keys_match_reference():
         m = CAVPInferenceB200()
     got = {k: tuple(v.shape) for k, v in m.state_dict().items() if "num_batches" not in k and k != "logit_scale"}
     assert got == dict(cavp_oracle.cavp_param_shapes())
+
+
+# --------------------------------------------------------- round 2: a16, N3 (DPM-Solver / PLMS), schedule length
+def test_cond_stage_oracle_matches_reference():
+    """Video_Feat_Encoder_Posembed (row a16): oracle vs the reference module's output (cond_embed.npz)."""
+    g = load("cond_embed")
+    sd = ddim_oracle.cond_stage_seeded_state(int(g["seed"]))
+    out = ddim_oracle.cond_stage(sd, torch.from_numpy(g["feats"]))
+    assert out.shape == (3, 32, 768)
+    assert rel_l2(out, g["out"]) < 2e-6
+
+
+def test_ddim_oracle_runs_every_schedule_entry_when_S_does_not_divide_1000():
+    """S = 30: c = 1000 // 30 = 33, range(0, 1000, 33) has 31 entries and the reference runs them all
+    (ddim.py:197-199) -- the round-1 fused sampler stopped after S."""
+    g = load("ddim_small_s30")
+    c = ddim_oracle.ddim_coefficients(int(g["steps"]))
+    assert len(c["timesteps"]) == len(range(0, 1000, 1000 // 30)) == 31
+    sd = unet_oracle.seeded_state_dict(SMALL, int(g["seed"]))
+    cond = torch.from_numpy(g["cond"])
+    fn = lambda x, t, cc: unet_oracle.unet_forward(sd, SMALL, x, t, cc)
+    x, _ = ddim_oracle.ddim_sample(fn, torch.from_numpy(g["x_T"]), cond, torch.zeros_like(cond), float(g["scale"]),
+                                   int(g["steps"]))
+    assert rel_l2(x, g["samples"]) < 2e-5
+
+
+@pytest.mark.parametrize("name", ["dpm_small", "dpm_small_s10"])
+def test_dpm_solver_oracle_matches_reference_sampler(name):
+    from oracle import dpm_oracle
+    g = load(name)
+    sd = unet_oracle.seeded_state_dict(SMALL, int(g["seed"]))
+    cond = torch.from_numpy(g["cond"])
+    fn = lambda x, t, cc: unet_oracle.unet_forward(sd, SMALL, x, t, cc)
+    x = dpm_oracle.dpm_solver_sample(fn, torch.from_numpy(g["x_T"]), cond, torch.zeros_like(cond), float(g["scale"]),
+                                     int(g["steps"]))
+    assert rel_l2(x, g["samples"]) < 5e-5
+
+
+def test_plms_oracle_matches_reference_sampler():
+    from oracle import dpm_oracle
+    g = load("plms_small")
+    sd = unet_oracle.seeded_state_dict(SMALL, int(g["seed"]))
+    cond = torch.from_numpy(g["cond"])
+    fn = lambda x, t, cc: unet_oracle.unet_forward(sd, SMALL, x, t, cc)
+    x, _ = dpm_oracle.plms_sample(fn, torch.from_numpy(g["x_T"]), cond, torch.zeros_like(cond), float(g["scale"]),
+                                  int(g["steps"]))
+    assert rel_l2(x, g["samples"]) < 5e-5
+
+
+@pytest.mark.parametrize("steps", [10, 25, 50])
+def test_dpm_host_schedule_equals_oracle_schedule(steps):
+    """diff_foley_b200/dpm_solver.py precomputes the per-step scalars the fused sampler consumes; they must be
+    the oracle's NoiseScheduleDiscrete evaluated at the same times (host logic, no GPU)."""
+    from diff_foley_b200.dpm_solver import dpm_solver_pp_2m_schedule
+    from oracle import dpm_oracle
+    ac = ddim_oracle.alphas_cumprod()
+    s = dpm_solver_pp_2m_schedule(ac, steps)
+    ns = dpm_oracle.NoiseScheduleDiscrete(ac)
+    t = torch.linspace(1.0, 1e-3, steps + 1)
+    assert np.allclose(s["t_cont"], t.numpy())
+    assert np.allclose(s["sigma"], ns.marginal_std(t[:-1]).numpy(), rtol=1e-6)
+    assert np.allclose(s["alpha"], ns.marginal_alpha(t[:-1]).numpy(), rtol=1e-6)
+    assert np.allclose(s["t_input"], ns.model_input_time(t[:-1]).numpy(), rtol=1e-6)
+    lam = ns.marginal_lambda(t)
+    h = lam[1:] - lam[:-1]
+    assert np.allclose(s["cx"], (ns.marginal_std(t[1:]) / ns.marginal_std(t[:-1])).numpy(), rtol=1e-6)
+    assert np.allclose(s["a_coef"], (ns.marginal_alpha(t[1:]) * torch.expm1(-h)).numpy(), rtol=2e-5)
+    assert s["order"][0] == 1 and (s["order"][1:-1] == 2).all() and s["order"][-1] == (1 if steps < 15 else 2)
+    assert np.allclose(s["inv_r0"][1:], (h[1:] / h[:-1]).numpy(), rtol=1e-5) and s["inv_r0"][0] == 0
+
+
+def test_dpm_host_loop_matches_reference_golden_with_oracle_unet():
+    """DPMSolverSamplerB200's host loop (the path classifier guidance takes) driven by the oracle UNet on CPU:
+    the sampler logic itself, independent of the kernels, against the reference sampler's latent."""
+    from diff_foley_b200.dpm_solver import DPMSolverSamplerB200
+    g = load("dpm_small_s10")
+    sd = unet_oracle.seeded_state_dict(SMALL, int(g["seed"]))
+
+    class Model:
+        alphas_cumprod = ddim_oracle.alphas_cumprod()
+        betas = torch.zeros(1)
+
+        @staticmethod
+        def apply_model(x, t, c):
+            return unet_oracle.unet_forward(sd, SMALL, x, t, c)
+
+    cond = torch.from_numpy(g["cond"])
+    x, _ = DPMSolverSamplerB200(Model()).sample(int(g["steps"]), 1, (4, SMALL["latent_h"], SMALL["latent_w"]), cond,
+                                                x_T=torch.from_numpy(g["x_T"]), unconditional_guidance_scale=float(g["scale"]),
+                                                unconditional_conditioning=torch.zeros_like(cond))
+    assert rel_l2(x, g["samples"]) < 5e-5

@@ -55,7 +55,9 @@ def test_unet_forward_matches_reference_golden(name, cfg):
     assert torch.isfinite(eps).all()
     err = rel_l2(eps, g["eps"])
     print(f"\n[parity] {name}: eps rel-L2 vs reference fp32 = {err:.3e}")
-    assert err < 3e-3
+    # measured 8.2e-4 .. 9.7e-4 (fp16 operand rounding through ~165 GEMMs, random U(+-1/sqrt(fan_in)) weights --
+    # the operand range of a real checkpoint is unverified here); bound = 1.5 x the worst measured
+    assert err < 1.5e-3
     # bit-reproducible (split-K reduces through DSMEM in rank order, no atomics) + launch count (no
     # silent fallback: the engine really launched its plan)
     eps2 = m(x, t, context=ctx)
@@ -75,7 +77,7 @@ def test_unet_float_timesteps_and_cached_context():
     tf = torch.tensor([333.25, 12.5])
     ref = unet_oracle.unet_forward(sd, SMALL, x.cpu(), tf, ctx.cpu())
     out = m(x, tf.cuda(), context=ctx)
-    assert rel_l2(out, ref) < 3e-3
+    assert rel_l2(out, ref) < 1.5e-3
 
 
 @pytest.mark.parametrize("name,cfg", [("ddim_small", SMALL), ("ddim_full", FULL)])
@@ -96,7 +98,10 @@ def test_fused_ddim_matches_reference_sampler(name, cfg):
     err = rel_l2(samples, g["samples"])
     err0 = rel_l2(inter["pred_x0"][-1], g["pred_x0"])
     print(f"\n[parity] {name}: latent after {int(g['steps'])} steps rel-L2 = {err:.3e}, pred_x0 = {err0:.3e}")
-    assert err < 2e-2
+    assert err < 1e-3 and err0 < 1e-3       # measured 3.3e-4 / 3.7e-4; the north-star bound itself
+    # intermediates like the reference's (ddim.py:223-226): x_T, after the first step, after the last
+    assert len(inter["x_inter"]) == 3 and len(inter["pred_x0"]) == 3
+    assert torch.equal(inter["x_inter"][-1], samples) and not torch.equal(inter["x_inter"][1], samples)
     if name == "ddim_full":
         # THE north-star number: rel-L2 on the decoded mel-spectrogram (channel 0 of the first-stage
         # decode), same decoder applied to both latents.  Decoder = pinned oracle.
@@ -129,7 +134,7 @@ def test_fused_ddim_matches_reference_sampler(name, cfg):
     # reference, about sqrt(2) x that noise apart.  Each path is bit-reproducible run to run.
     print(f"[parity] {name}: fused vs host-loop rel-L2 = {rel_l2(samples2, samples):.3e}")
     assert rel_l2(samples2, samples) < 1e-3
-    assert rel_l2(samples2, g["samples"]) < 2e-2
+    assert rel_l2(samples2, g["samples"]) < 1e-3
     samples3, _ = ldm.sample_log_diff_sampler(cond, n, "DDIM", int(g["steps"]), size_len=cfg["latent_w"],
                                               unconditional_guidance_scale=float(g["scale"]),
                                               unconditional_conditioning=torch.zeros_like(cond), x_T=x_T)
@@ -149,7 +154,7 @@ def test_sharded_sampler_world1_matches_fused():
     torch.cuda.synchronize()
     err = rel_l2(out, g["samples"])
     print(f"\n[parity] sharded sampler (world 1): latent rel-L2 = {err:.3e}")
-    assert err < 2e-2
+    assert err < 1e-3
 
 
 def test_classifier_guided_sampling_matches_reference():
@@ -183,7 +188,7 @@ def test_classifier_guided_sampling_matches_reference():
     torch.cuda.synchronize()
     err = rel_l2(samples, g["samples"])
     print(f"\n[parity] classifier-guided DDIM-25: latent rel-L2 = {err:.3e}")
-    assert err < 2e-2
+    assert err < 1e-3
 
 
 def test_in_kernel_timeline():
@@ -208,3 +213,132 @@ def test_in_kernel_timeline():
     assert (w[1:] >= w[:-1]).all()              # dependent launches release in order
     assert 0 < (x_.max() - e.min()) < 50_000_000  # one small forward: well under 50 ms
     assert torch.equal(unet(x, t, context=ctx), before)
+
+
+# ------------------------------------------------------------------------------------ round 2 additions
+def test_block_taps_match_reference_golden():
+    """The 7 block outputs stored in unet_small.npz (reference forward hooks) against the CUDA engine's
+    block outputs (dfb_unet_debug_tap): localises an error to a block, not just to the final eps."""
+    import os as _os
+    g = np.load(os.path.join(GOLD, "unet_small.npz"))
+    _os.environ["DFB_DEBUG_TAPS"] = "1"      # keep every block output alive (no rotating-buffer reuse)
+    try:
+        m = UNetModelB200(**unet_kwargs(SMALL))
+        m.load_state_dict(unet_oracle.seeded_state_dict(SMALL, int(g["seed"])), strict=True)
+        m = m.cuda()
+        x, t, ctx = (torch.from_numpy(g[k]).cuda() for k in ("x", "t", "ctx"))
+        m(x, t, context=ctx)
+        taps = m.debug_taps(x.shape[0])
+    finally:
+        _os.environ.pop("DFB_DEBUG_TAPS", None)
+    checked = 0
+    for k in g.files:
+        if k.startswith("tap:"):
+            err = rel_l2(taps[k[4:]], g[k])
+            print(f"[parity] tap {k[4:]}: rel-L2 {err:.3e}")
+            assert err < 1.5e-3, k
+            checked += 1
+    assert checked == 7
+
+
+def test_cond_stage_embedder_matches_reference():
+    """Row a16: LatentDiffusionB200.get_learned_conditioning (Linear 512->768 on the tcgen05 GEMM + positional
+    rows as the residual epilogue) against the reference's Video_Feat_Encoder_Posembed output."""
+    from oracle import ddim_oracle
+    g = np.load(os.path.join(GOLD, "cond_embed.npz"))
+    ldm = LatentDiffusionB200(model_for(SMALL, 1), cond_stage_params=dict(origin_dim=512, embed_dim=768, seq_len=40))
+    ldm.cond_stage_model.load_state_dict(ddim_oracle.cond_stage_seeded_state(int(g["seed"])), strict=True)
+    ldm = ldm.cuda()
+    out = ldm.get_learned_conditioning(torch.from_numpy(g["feats"]).cuda())
+    torch.cuda.synchronize()
+    err = rel_l2(out, g["out"])
+    print(f"\n[parity] cond-stage embedder: rel-L2 = {err:.3e}")
+    assert out.shape == (3, 32, 768) and err < 5e-4      # fp16 operands, K = 512
+
+
+def test_fused_ddim_runs_every_schedule_entry():
+    """S = 30 does not divide 1000: the schedule has 31 entries and the reference runs all of them."""
+    g = np.load(os.path.join(GOLD, "ddim_small_s30.npz"))
+    unet = model_for(SMALL, int(g["seed"]))
+    ldm = LatentDiffusionB200(unet, cond_stage_params=dict(origin_dim=64, embed_dim=SMALL["context_dim"], seq_len=40)).cuda()
+    cond, x_T = torch.from_numpy(g["cond"]).cuda(), torch.from_numpy(g["x_T"]).cuda()
+    out, _ = ldm.sample_log_diff_sampler(cond, 1, "DDIM", int(g["steps"]), size_len=SMALL["latent_w"],
+                                         unconditional_guidance_scale=float(g["scale"]),
+                                         unconditional_conditioning=torch.zeros_like(cond), x_T=x_T)
+    torch.cuda.synchronize()
+    err = rel_l2(out, g["samples"])
+    print(f"\n[parity] DDIM S=30 (31 schedule entries): latent rel-L2 = {err:.3e}")
+    assert err < 1e-3
+    with pytest.raises(ValueError):       # raw pointers cross the ABI: extents are validated first (ADVICE r1)
+        ldm.sample_log_diff_sampler(cond, 1, "DDIM", 5, size_len=SMALL["latent_w"] * 2, unconditional_guidance_scale=4.5,
+                                    unconditional_conditioning=torch.zeros_like(cond))
+    with pytest.raises(ValueError):
+        ldm.sample_log_diff_sampler(cond, 2, "DDIM", 5, size_len=SMALL["latent_w"], unconditional_guidance_scale=4.5,
+                                    unconditional_conditioning=torch.zeros_like(cond), x_T=x_T)
+
+
+@pytest.mark.parametrize("name", ["dpm_small", "dpm_small_s10"])
+def test_dpm_solver_matches_reference_sampler(name):
+    """N3: the notebook's default sampler (DPM-Solver++ 2M, fractional fp32 timesteps) as one fused C call vs the
+    reference's DPMSolverSampler latent; the host-loop path (what classifier guidance uses) must agree."""
+    from diff_foley_b200.dpm_solver import DPMSolverSamplerB200
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    unet = model_for(SMALL, int(g["seed"]))
+    ldm = LatentDiffusionB200(unet, cond_stage_params=dict(origin_dim=64, embed_dim=SMALL["context_dim"], seq_len=40)).cuda()
+    cond, x_T = torch.from_numpy(g["cond"]).cuda(), torch.from_numpy(g["x_T"]).cuda()
+    n = x_T.shape[0]
+    kw = dict(size_len=SMALL["latent_w"], unconditional_guidance_scale=float(g["scale"]),
+              unconditional_conditioning=torch.zeros_like(cond), x_T=x_T)
+    out, _ = ldm.sample_log_diff_sampler(cond, n, "DPM_Solver", int(g["steps"]), **kw)
+    torch.cuda.synchronize()
+    err = rel_l2(out, g["samples"])
+    out2, _ = DPMSolverSamplerB200(ldm).sample(int(g["steps"]), n, (4, SMALL["latent_h"], SMALL["latent_w"]), cond,
+                                               x_T=x_T, unconditional_guidance_scale=float(g["scale"]),
+                                               unconditional_conditioning=torch.zeros_like(cond), callback=lambda k: None)
+    torch.cuda.synchronize()
+    err2 = rel_l2(out2, g["samples"])
+    print(f"\n[parity] {name}: fused DPM-Solver++ rel-L2 = {err:.3e}, host loop = {err2:.3e}")
+    assert err < 1e-3 and err2 < 1e-3
+    again, _ = ldm.sample_log_diff_sampler(cond, n, "DPM_Solver", int(g["steps"]), **kw)
+    assert torch.equal(again, out)
+
+
+def test_plms_matches_reference_sampler():
+    g = np.load(os.path.join(GOLD, "plms_small.npz"))
+    unet = model_for(SMALL, int(g["seed"]))
+    ldm = LatentDiffusionB200(unet, cond_stage_params=dict(origin_dim=64, embed_dim=SMALL["context_dim"], seq_len=40)).cuda()
+    cond, x_T = torch.from_numpy(g["cond"]).cuda(), torch.from_numpy(g["x_T"]).cuda()
+    out, inter = ldm.sample_log_diff_sampler(cond, x_T.shape[0], "PLMS", int(g["steps"]), size_len=SMALL["latent_w"],
+                                             unconditional_guidance_scale=float(g["scale"]),
+                                             unconditional_conditioning=torch.zeros_like(cond), x_T=x_T)
+    torch.cuda.synchronize()
+    err = rel_l2(out, g["samples"])
+    print(f"\n[parity] PLMS-25: latent rel-L2 = {err:.3e}")
+    assert err < 1e-3 and len(inter["x_inter"]) == 3
+
+
+def test_classifier_guided_sampling_full_width():
+    """BASELINE config 3's scheme at FULL width: the 859.5 M UNet + the 11.45 M classifier, CFG 4.5 +
+    classifier guidance 50, 5 DDIM steps, vs the reference's sample_with_classifier (CPU fp32)."""
+    from diff_foley_b200.classifier import AlignmentClassifierDoubleGuidanceB200
+    from oracle import classifier_oracle
+    g = np.load(os.path.join(GOLD, "ddim_classifier_full.npz"))
+    unet = model_for(FULL, int(g["seed"]))
+    ldm = LatentDiffusionB200(unet).cuda()
+    clf = AlignmentClassifierDoubleGuidanceB200()
+    clf.model.load_state_dict(classifier_oracle.seeded_state_dict(classifier_oracle.DIFF_FOLEY_CLASSIFIER, int(g["seed"]) + 1))
+    clf = clf.cuda()
+    cond, feats, x_T = (torch.from_numpy(g[k]).cuda() for k in ("cond", "feats", "x_T"))
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        samples, _ = ldm.sample_log_with_classifier_diff_sampler(
+            cond, feats, 1, "DDIM", int(g["steps"]), unconditional_guidance_scale=float(g["scale"]),
+            unconditional_conditioning=torch.zeros_like(cond), classifier=clf, classifier_guide_scale=float(g["cscale"]),
+            x_T=x_T)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    torch.cuda.synchronize()
+    err = rel_l2(samples, g["samples"])
+    print(f"\n[parity] full-width classifier-guided DDIM-5: latent rel-L2 = {err:.3e}")
+    assert err < 1e-3
