@@ -56,6 +56,7 @@ SIGNATURES = {
                              C.POINTER(_f), C.POINTER(_f), _fp, _fp, _fp, _vp]),
     "dfb_dpm_solver_sample": (_i, [_vp, _fp, _fp, _fp, _i, _i, _f, _i, C.POINTER(_f), C.POINTER(_f), C.POINTER(_f),
                                    C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), C.POINTER(C.c_int32), _fp, _vp]),
+    "dfb_frames_resize": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _fp, _vp, _vp]),
     "dfb_comm_unique_id": (_i, [_vp]),
     "dfb_comm_init": (_i, [_vp, _i, _i, _vp]),
     "dfb_comm_destroy": (_i, [_vp]),

@@ -163,6 +163,17 @@ int dfb_conv_taps(const void* a, const void* w, int B, int T, int H, int W, int 
 
 void dfb_debug_igemm_force(int bn, int deep) { igemm_force(bn, deep); }
 
+int dfb_frames_resize(const void* src_u8, int N, int H, int W, int swap_rb, const int32_t* kk_h, const int32_t* bounds_h,
+                      int ksize_h, int OW, const int32_t* kk_v, const int32_t* bounds_v, int ksize_v, int OH,
+                      void* tmp_u8, float* out_f32, void* out_u8, void* stream) {
+  if (!src_u8 || !kk_h || !bounds_h || !kk_v || !bounds_v || !tmp_u8 || !out_f32 || N < 1 || H < 1 || W < 1 || OW < 1 ||
+      OH < 1 || ksize_h < 1 || ksize_v < 1) { set_error("dfb_frames_resize: bad argument"); return DFB_E_INVALID; }
+  int r = kernels_init();
+  if (r) return r;
+  return frames_resize_launch((const uint8_t*)src_u8, N, H, W, swap_rb, kk_h, bounds_h, ksize_h, OW, kk_v, bounds_v,
+                              ksize_v, OH, (uint8_t*)tmp_u8, out_f32, (uint8_t*)out_u8, (cudaStream_t)stream);
+}
+
 int dfb_im2col_f16(const void* src, void* dst, int NI, int H, int W, int C, int kh, int kw, int stride,
                    int pad, int Kpad, void* stream) {
   return im2col_f16_launch((const __half*)src, (__half*)dst, NI, H, W, C, kh, kw, stride, pad, Kpad,

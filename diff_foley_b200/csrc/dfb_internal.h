@@ -192,6 +192,10 @@ int im2col_f16_launch(const __half* src, __half* dst, int NI, int H, int W, int 
 // max / average pooling over [NI,H,W,C]; window (kh,kw), stride (sh,sw), padding (ph,pw)
 int pool2d_f16_launch(const __half* src, __half* dst, int NI, int H, int W, int C, int kh, int kw,
                       int sh, int sw, int ph, int pw, int is_max, cudaStream_t stream);
+// CAVP frame ingest: Pillow-exact two-pass 8-bit bilinear resample of N uint8 HWC frames + ToTensor
+int frames_resize_launch(const uint8_t* src, int N, int H, int W, int swap_rb, const int* kk_h, const int* bounds_h,
+                         int ksize_h, int OW, const int* kk_v, const int* bounds_v, int ksize_v, int OH, uint8_t* tmp,
+                         float* out, uint8_t* out_u8, cudaStream_t stream);
 // fused classifier-free-guidance combine + DDIM update (ddim.py:241-273 of the reference)
 int ddim_update_launch(const float* x, const float* eps_uncond, const float* eps_cond,
                        const float* grad, float cfg_scale, float sqrt_one_minus_at, float sqrt_at,

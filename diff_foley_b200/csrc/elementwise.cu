@@ -370,6 +370,81 @@ int ddim_update_launch(const float* x, const float* eps_uncond, const float* eps
   return 0;
 }
 
+// ---- CAVP frame ingest (row N4; reference inference/demo_util.py:135-163: per frame cv2 BGR->RGB, PIL
+// Resize((224,224)) = Pillow's two-pass antialiased bilinear resample in 8-bit fixed point, ToTensor).
+// Pillow's arithmetic (src/libImaging/Resample.c: ImagingResampleHorizontal_8bpc / Vertical_8bpc): per output
+// sample  clip8((2^21 + sum_x pix[xmin + x] * k[x]) >> 22)  with int32 coefficients k = round(w * 2^22), the
+// horizontal pass rounded to uint8 before the vertical one.  The host builds the coefficient tables exactly as
+// precompute_coeffs / normalize_coeffs_8bpc do (diff_foley_b200/frames.py); these kernels do the integer MACs,
+// so the result is bit-identical to PIL for every frame size.  A whole window of frames is one launch pair.
+__device__ __forceinline__ int clip8_fixed(int v) {
+  v >>= 22;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+// in [N,H,W,3] u8 -> tmp [N,H,OW,3] u8 (channel order swapped when swap_rb: cv2 delivers BGR)
+__global__ void resample_h_u8_kernel(const uint8_t* __restrict__ in, int H, int W, int OW, int swap_rb,
+                                     const int* __restrict__ kk, const int* __restrict__ bounds, int ksize,
+                                     uint8_t* __restrict__ tmp, long total) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;   // (n*H + y) * OW + ox
+  if (i >= total) return;
+  const int ox = (int)(i % OW);
+  const long row = i / OW;
+  const int xmin = bounds[2 * ox], xmax = bounds[2 * ox + 1];
+  const int* k = kk + (long)ox * ksize;
+  const uint8_t* src = in + (row * W + xmin) * 3;
+  int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+  for (int x = 0; x < xmax; ++x) {
+    const int c = k[x];
+    s0 += src[3 * x + 0] * c;
+    s1 += src[3 * x + 1] * c;
+    s2 += src[3 * x + 2] * c;
+  }
+  uint8_t* d = tmp + i * 3;
+  d[swap_rb ? 2 : 0] = (uint8_t)clip8_fixed(s0);
+  d[1] = (uint8_t)clip8_fixed(s1);
+  d[swap_rb ? 0 : 2] = (uint8_t)clip8_fixed(s2);
+}
+// tmp [N,H,OW,3] u8 -> out [N,3,OH,OW] fp32 in [0,1] (ToTensor: x / 255), optionally the uint8 image too
+__global__ void resample_v_u8_kernel(const uint8_t* __restrict__ tmp, int H, int OW, int OH,
+                                     const int* __restrict__ kk, const int* __restrict__ bounds, int ksize,
+                                     float* __restrict__ out, uint8_t* __restrict__ out_u8, long total) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;   // (n*OH + oy) * OW + ox
+  if (i >= total) return;
+  const int ox = (int)(i % OW);
+  const int oy = (int)((i / OW) % OH);
+  const long n = i / ((long)OW * OH);
+  const int ymin = bounds[2 * oy], ymax = bounds[2 * oy + 1];
+  const int* k = kk + (long)oy * ksize;
+  const uint8_t* src = tmp + ((n * H + ymin) * OW + ox) * 3;
+  int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+  for (int y = 0; y < ymax; ++y) {
+    const int c = k[y];
+    const uint8_t* q = src + (long)y * OW * 3;
+    s0 += q[0] * c;
+    s1 += q[1] * c;
+    s2 += q[2] * c;
+  }
+  const int v0 = clip8_fixed(s0), v1 = clip8_fixed(s1), v2 = clip8_fixed(s2);
+  const long plane = (long)OH * OW, o = n * 3 * plane + (long)oy * OW + ox;
+  out[o] = __fdiv_rn((float)v0, 255.f);
+  out[o + plane] = __fdiv_rn((float)v1, 255.f);
+  out[o + 2 * plane] = __fdiv_rn((float)v2, 255.f);
+  if (out_u8 != nullptr) { out_u8[i * 3] = (uint8_t)v0; out_u8[i * 3 + 1] = (uint8_t)v1; out_u8[i * 3 + 2] = (uint8_t)v2; }
+}
+
+int frames_resize_launch(const uint8_t* src, int N, int H, int W, int swap_rb, const int* kk_h, const int* bounds_h,
+                         int ksize_h, int OW, const int* kk_v, const int* bounds_v, int ksize_v, int OH, uint8_t* tmp,
+                         float* out, uint8_t* out_u8, cudaStream_t stream) {
+  const long t1 = (long)N * H * OW, t2 = (long)N * OH * OW;
+  note("frames_resize", 0.0, (double)N * H * W * 3 + 2.0 * t1 * 3 + t2 * 12.0);
+  DFB_CUDA_OK(launch_pdl(resample_h_u8_kernel, dim3((unsigned)((t1 + 255) / 256)), dim3(256), 0, stream, src, H, W, OW,
+                         swap_rb, kk_h, bounds_h, ksize_h, tmp, t1));
+  DFB_CUDA_OK(launch_pdl(resample_v_u8_kernel, dim3((unsigned)((t2 + 255) / 256)), dim3(256), 0, stream,
+                         (const uint8_t*)tmp, H, OW, OH, kk_v, bounds_v, ksize_v, out, out_u8, t2));
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int elementwise_init() {
 #define DFB_MAXSHARED(k) \
   DFB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))

@@ -104,6 +104,16 @@ int dfb_dpm_solver_sample(dfb_handle h, float* x_dev, const float* cond_dev, con
                           int n_clips, int ctx_len, float cfg_scale, int n_evals, const float* t_input,
                           const float* sigma, const float* alpha, const float* cx, const float* a_coef,
                           const float* inv_r0, const int32_t* order, float* pred_x0_dev, void* stream);
+/* CAVP frame ingest (reference inference/demo_util.py:135-163: cv2 BGR->RGB, PIL Resize((224,224)), ToTensor).
+ * src: N uint8 frames [N,H,W,3] on the device (swap_rb = 1 for cv2's BGR order).  kk_* / bounds_* are the
+ * int32 coefficient tables of Pillow's resample for (W -> OW) and (H -> OH) (precompute_coeffs +
+ * normalize_coeffs_8bpc, built by diff_foley_b200/frames.py), on the device: kk [O, ksize], bounds [O, 2] =
+ * (first source index, count).  tmp_u8: [N,H,OW,3] scratch.  out_f32: [N,3,OH,OW] in [0,1] -- bit-identical
+ * to ToTensor()(PIL resize); out_u8 (optional): the resized uint8 image [N,OH,OW,3]. */
+int dfb_frames_resize(const void* src_u8_dev, int N, int H, int W, int swap_rb, const int32_t* kk_h_dev,
+                      const int32_t* bounds_h_dev, int ksize_h, int OW, const int32_t* kk_v_dev,
+                      const int32_t* bounds_v_dev, int ksize_v, int OH, void* tmp_u8_dev, float* out_f32_dev,
+                      void* out_u8_dev, void* stream);
 /* Multi-GPU (one process per GPU): the library owns its NCCL communicator, created from a 128-byte
  * ncclUniqueId that rank 0 obtains with dfb_comm_unique_id and the host distributes (e.g. a
  * torch.distributed broadcast); freed by dfb_comm_destroy / dfb_unet_destroy. */

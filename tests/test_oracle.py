@@ -267,3 +267,32 @@ def test_dpm_host_loop_matches_reference_golden_with_oracle_unet():
                                                 x_T=torch.from_numpy(g["x_T"]), unconditional_guidance_scale=float(g["scale"]),
                                                 unconditional_conditioning=torch.zeros_like(cond))
     assert rel_l2(x, g["samples"]) < 5e-5
+
+
+# -------------------------------------------------------------------------- N4: CAVP frame ingest (Pillow resample)
+@pytest.mark.parametrize("H,W", [(360, 640), (100, 150), (224, 224), (480, 227), (720, 1280), (37, 53)])
+def test_frames_oracle_is_bit_identical_to_pillow(H, W):
+    """The frame preprocessing of Extract_CAVP_Features (demo_util.py:147-150) is Pillow arithmetic: the numpy
+    restatement (oracle/frames_oracle.py) must reproduce PIL Resize + ToTensor bit for bit, up- and down-scaling."""
+    from PIL import Image
+    import torchvision.transforms as T
+    from oracle import frames_oracle
+    rng = np.random.default_rng(H * 1000 + W)
+    bgr = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    ref = T.Compose([T.Resize((224, 224)), T.ToTensor()])(Image.fromarray(np.ascontiguousarray(bgr[:, :, ::-1]))).numpy()
+    got = frames_oracle.preprocess_frame(bgr)
+    assert got.dtype == np.float32 and got.shape == (3, 224, 224)
+    assert np.array_equal(ref, got)
+
+
+@pytest.mark.parametrize("n_in", [640, 360, 224, 150, 100, 53, 1920])
+def test_frames_host_tables_equal_oracle_tables(n_in):
+    """The product builds Pillow's fixed-point coefficient tables vectorised (diff_foley_b200/frames.py); they must
+    equal the oracle's loop restatement of precompute_coeffs + normalize_coeffs_8bpc, and each row sums to ~2^22."""
+    from diff_foley_b200.frames import _bilinear_tables
+    from oracle import frames_oracle
+    k1, b1, s1 = frames_oracle.precompute_coeffs(n_in, 224)
+    k2, b2, s2 = _bilinear_tables(n_in, 224)
+    assert s1 == s2 and np.array_equal(b1, b2) and np.array_equal(k1, k2)
+    assert np.all(np.abs(k2.astype(np.int64).sum(1) - (1 << 22)) <= k2.shape[1])
+    assert np.all(b2[:, 0] >= 0) and np.all(b2[:, 0] + b2[:, 1] <= n_in) and np.all(b2[:, 1] >= 1)
