@@ -56,6 +56,18 @@ SIGNATURES = {
                              C.POINTER(_f), C.POINTER(_f), _fp, _fp, _fp, _vp]),
     "dfb_dpm_solver_sample": (_i, [_vp, _fp, _fp, _fp, _i, _i, _f, _i, C.POINTER(_f), C.POINTER(_f), C.POINTER(_f),
                                    C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), C.POINTER(C.c_int32), _fp, _vp]),
+    "dfb_groupnorm_bwd": (_i, [_fp, _i, _i, _i, _fp, _fp, _f, _i, _fp, _fp, _fp, _vp, _vp]),
+    "dfb_layernorm_bwd": (_i, [_fp, _i, _i, _fp, _f, _fp, _fp, _fp, _vp, _vp]),
+    "dfb_attention_bwd": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _fp, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _vp, _i,
+                               _vp, _i, _fp, _fp, _vp]),
+    "dfb_geglu_fwd": (_i, [_fp, C.c_longlong, _i, _vp, _vp]),
+    "dfb_geglu_bwd": (_i, [_fp, _fp, C.c_longlong, _i, _vp, _vp]),
+    "dfb_col2im_s2": (_i, [_fp, _i, _i, _i, _i, _fp, _fp, _vp, _vp]),
+    "dfb_classifier_head": (_i, [_fp, _i, _i, _i, _fp, _fp, _f, _fp, _vp, _vp]),
+    "dfb_scale_f32": (_i, [_fp, _f, C.c_longlong, _vp]),
+    "dfb_cast_f16": (_i, [_fp, _vp, C.c_longlong, _vp]),
+    "dfb_stem_conv": (_i, [_fp, _i, _i, _i, _i, _fp, _fp, _i, _fp, _vp]),
+    "dfb_head_conv": (_i, [_vp, _i, _i, _i, _i, _fp, _fp, _i, _fp, _vp]),
     "dfb_frames_resize": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _fp, _vp, _vp]),
     "dfb_comm_unique_id": (_i, [_vp]),
     "dfb_comm_init": (_i, [_vp, _i, _i, _vp]),

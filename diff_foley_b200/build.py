@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libdfb.so")
-SOURCES = ["igemm_tcgen05.cu", "norm.cu", "attention_tcgen05.cu", "elementwise.cu", "engine.cu", "capi.cu"]
+SOURCES = ["igemm_tcgen05.cu", "norm.cu", "attention_tcgen05.cu", "elementwise.cu", "backward.cu", "engine.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",

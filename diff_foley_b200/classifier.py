@@ -1,22 +1,34 @@
-"""Double-guidance alignment classifier (SURVEY row a15): same parameter names / call signature as the
+"""Double-guidance alignment classifier (SURVEY rows a15 / N2): same parameter names / call signature as the
 reference's `Alignment_Classifier_Double_Guidance` + `Classifier_Backbone`
 (diff_foley/modules/double_guidance/alignment_classifier.py:72-295, alignment_backbone.py:417-686).
 
-STATUS -- the one part of the hot path that is NOT on hand-written kernels yet.  Classifier guidance
-needs d/dx of log p(x_t, t, video_feat) through this half-UNet every step (ddim.py:333-341), i.e.
-forward AND backward of conv / GroupNorm / attention.  Backward kernels are the "next" item N2 of the
-scope table; until they exist the classifier forward/backward runs on torch autograd (cuDNN / cuBLAS
-library kernels on the GPU -- never the CPU, never the oracle).  It is 2.4 % of the per-step FLOPs
-(2 x 2.87 GFLOP vs 355.7).  What is native already: the guided update itself
-(`dfb_ddim_step(..., grad, grad_coef)`, ddim.py:377-395) and the UNet the gradient is added to.
+Classifier guidance needs d/dx of log p(x_t, t, video_feat) through this half-UNet every step
+(ddim.py:333-341: torch.autograd.grad).  On a CUDA device `loglikelihood_grad` computes it with the hand-written
+kernels only -- a hand-derived forward + backward over the C ABI, no autograd, no cuDNN / cuBLAS:
+  * every conv / Linear, forward and backward-data, is the tcgen05 implicit GEMM (`dfb_conv3x3`, `dfb_gemm`); the
+    backward passes use weights packed once in rotated (3x3: taps flipped, in/out swapped) or transposed form;
+  * GroupNorm(+SiLU) / LayerNorm forward are the UNet's kernels, their backward `dfb_groupnorm_bwd` /
+    `dfb_layernorm_bwd` (statistics recomputed from the saved input, residual-branch sum fused);
+  * attention forward is the fused tcgen05 kernel, backward `dfb_attention_bwd` (deterministic, two kernels);
+  * GEGLU, the stride-2 conv's scatter (as a gather), avg-pool + Linear + sigmoid + log and the gradient seed are
+    small kernels in csrc/backward.cu; the 4-channel stem and its backward are the boundary conv kernels.
+Gradients that feed a GEMM travel in fp16 scaled by LOSS_SCALE (undone at the NCHW boundary); residual-path sums
+stay fp32.  The module's plain `forward` (torch functional ops, used for CPU checks of the parameter layout against
+the oracle) is not on the sampling path.
 """
 import math
+
+import ctypes as C
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib as L
 from .unet import _Box, _Holder, _res, _st
+
+LOSS_SCALE = 64.0   # fp16 gradient operands: keeps the seed (~scale * w / HW) well inside the normal range
+SILU, NOACT = 1, 0
 
 
 def _timestep_embedding(t, dim, max_period=10000):
@@ -143,6 +155,286 @@ class ClassifierBackboneB200(nn.Module):
         return torch.sigmoid(F.linear(h, self.classifier.weight, self.classifier.bias))
 
 
+# ================================================================ native forward + backward (CUDA only)
+def _e(shape, dev, dtype=torch.float32):
+    return torch.empty(shape, device=dev, dtype=dtype)
+
+
+class _Native:
+    """Packed weights + the op wrappers of one ClassifierBackboneB200 on one device."""
+
+    def __init__(self, m, dev):
+        self.m, self.dev, self.lib = m, dev, L.lib()
+        self.heads = m.num_heads
+        h16 = lambda t: t.detach().to(dev, torch.float32).contiguous().half().contiguous()
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        self.w = {}
+
+        def conv3(path, mod):
+            w = mod.weight.detach().to(dev, torch.float32)
+            self.w[path] = dict(f=h16(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)),
+                                b=h16(w.flip(2, 3).permute(1, 2, 3, 0).reshape(w.shape[1], -1)),
+                                bias=f32(mod.bias), cout=w.shape[0], cin=w.shape[1])
+
+        def lin(path, mod, bias=True):
+            w = mod.weight.detach().to(dev, torch.float32).reshape(mod.weight.shape[0], -1)
+            self.w[path] = dict(f=h16(w), b=h16(w.t()), bias=f32(mod.bias) if bias and mod.bias is not None else None,
+                                n=w.shape[0], k=w.shape[1])
+
+        def norm(path, mod):
+            self.w[path] = dict(g=f32(mod.weight), b=f32(mod.bias))
+
+        lin("time_embed.0", m.time_embed[0]); lin("time_embed.2", m.time_embed[2])
+        stem = m.input_blocks[0][0]
+        sw = stem.weight.detach().to(dev, torch.float32)
+        self.w["stem"] = dict(f=f32(sw.permute(1, 2, 3, 0).reshape(-1, sw.shape[0])), bias=f32(stem.bias),
+                              b=f32(sw.flip(2, 3).permute(1, 2, 3, 0).reshape(sw.shape[1], 9, sw.shape[0])),
+                              zb=torch.zeros(sw.shape[1], device=dev), cout=sw.shape[0], cin=sw.shape[1])
+        for blk in m._layout:
+            for kind, path in blk:
+                mod = m.get_submodule(path)
+                if kind == "res":
+                    norm(path + ".gn1", mod.in_layers[0]); conv3(path + ".conv1", mod.in_layers[2])
+                    lin(path + ".emb", mod.emb_layers[1])
+                    norm(path + ".gn2", mod.out_layers[0]); conv3(path + ".conv2", mod.out_layers[3])
+                    if hasattr(mod, "skip_connection"):
+                        lin(path + ".skip", mod.skip_connection)
+                elif kind == "st":
+                    t = mod.transformer_blocks[0]
+                    norm(path + ".gn", mod.norm); lin(path + ".proj_in", mod.proj_in); lin(path + ".proj_out", mod.proj_out)
+                    for i, n in enumerate((t.norm1, t.norm2, t.norm3)):
+                        norm(path + f".ln{i + 1}", n)
+                    qkv = torch.cat([t.attn1.to_q.weight, t.attn1.to_k.weight, t.attn1.to_v.weight]).detach().to(dev, torch.float32)
+                    self.w[path + ".qkv"] = dict(f=h16(qkv), b=h16(qkv.t()), bias=None)
+                    lin(path + ".out1", t.attn1.to_out[0])
+                    lin(path + ".q2", t.attn2.to_q, bias=False)
+                    kv = torch.cat([t.attn2.to_k.weight, t.attn2.to_v.weight]).detach().to(dev, torch.float32)
+                    self.w[path + ".kv"] = dict(f=h16(kv), bias=None)
+                    lin(path + ".out2", t.attn2.to_out[0])
+                    lin(path + ".geglu", t.ff.net[0].proj); lin(path + ".ffout", t.ff.net[2])
+                elif kind == "down":
+                    conv3(path, mod)
+                    self.w[path]["bt"] = self.w[path]["f"].t().contiguous()      # dcol = dY . W  ->  "Wt" = W^T [9C, Cout]
+        norm("out.gn", m.out[0]); conv3("out.conv", m.out[2])
+        self.w["cls"] = dict(w=f32(m.classifier.weight.reshape(-1)), bias=f32(m.classifier.bias.reshape(-1)))
+
+    # ---- op wrappers (every one is a C-ABI call on the current stream)
+    def gemm(self, a16, w16, bias=None, residual=None, act=NOACT, o32=True, o16=False):
+        M, K = a16.shape
+        N = w16.shape[0]
+        out32 = _e((M, N), self.dev) if o32 else None
+        out16 = _e((M, N), self.dev, torch.float16) if o16 else None
+        L.check(self.lib.dfb_gemm(L.ptr(a16), L.ptr(w16), M, N, K, L.ptr(bias), L.ptr(residual), act, L.ptr(out32),
+                                  L.ptr(out16), 0, L.cur_stream()), "dfb_gemm")
+        return out32, out16
+
+    def conv3(self, a16, w16, B, H, W, bias=None, rowvec=None, residual=None, o32=True, o16=False):
+        Cc = a16.shape[-1]
+        N = w16.shape[0]
+        out32 = _e((B * H * W, N), self.dev) if o32 else None
+        out16 = _e((B * H * W, N), self.dev, torch.float16) if o16 else None
+        L.check(self.lib.dfb_conv3x3(L.ptr(a16), L.ptr(w16), B, H, W, Cc, N, L.ptr(bias), L.ptr(rowvec), L.ptr(residual),
+                                     NOACT, L.ptr(out32), L.ptr(out16), 0, L.cur_stream()), "dfb_conv3x3")
+        return out32, out16
+
+    def gn(self, x32, Cc, B, HW, p, eps, silu):
+        out = _e((B * HW, Cc), self.dev, torch.float16)
+        L.check(self.lib.dfb_groupnorm(L.ptr(x32), Cc, None, 0, B, HW, L.ptr(p["g"]), L.ptr(p["b"]), eps, silu, L.ptr(out),
+                                       None, L.cur_stream()), "dfb_groupnorm")
+        return out
+
+    def gn_bwd(self, x32, Cc, B, HW, p, eps, silu, dy, add, o32=True, o16=True):
+        d32 = _e((B * HW, Cc), self.dev) if o32 else None
+        d16 = _e((B * HW, Cc), self.dev, torch.float16) if o16 else None
+        L.check(self.lib.dfb_groupnorm_bwd(L.ptr(x32), Cc, B, HW, L.ptr(p["g"]), L.ptr(p["b"]), eps, silu, L.ptr(dy),
+                                           L.ptr(add), L.ptr(d32), L.ptr(d16), L.cur_stream()), "dfb_groupnorm_bwd")
+        return d32, d16
+
+    def ln(self, x32, p):
+        rows, Cc = x32.shape
+        out = _e((rows, Cc), self.dev, torch.float16)
+        L.check(self.lib.dfb_layernorm(L.ptr(x32), rows, Cc, L.ptr(p["g"]), L.ptr(p["b"]), 1e-5, L.ptr(out), L.cur_stream()),
+                "dfb_layernorm")
+        return out
+
+    def ln_bwd(self, x32, p, dy, add):
+        rows, Cc = x32.shape
+        d32, d16 = _e((rows, Cc), self.dev), _e((rows, Cc), self.dev, torch.float16)
+        L.check(self.lib.dfb_layernorm_bwd(L.ptr(x32), rows, Cc, L.ptr(p["g"]), 1e-5, L.ptr(dy), L.ptr(add), L.ptr(d32),
+                                           L.ptr(d16), L.cur_stream()), "dfb_layernorm_bwd")
+        return d32, d16
+
+    def attn(self, q, ldq, k, ldk, v, ldv, B, Lq, Lk, d):
+        Cc = self.heads * d
+        out = _e((B * Lq, Cc), self.dev, torch.float16)
+        L.check(self.lib.dfb_attention(L.ptr(q), ldq, L.ptr(k), ldk, L.ptr(v), ldv, L.ptr(out), Cc, B, self.heads, Lq, Lk, d, d,
+                                       d ** -0.5, L.cur_stream()), "dfb_attention")
+        return out
+
+    def attn_bwd(self, q, ldq, k, ldk, v, ldv, o, dO, B, Lq, Lk, d, dq, lddq, dk=None, lddk=0, dv=None, lddv=0):
+        Cc = self.heads * d
+        ws = _e((2, B * self.heads * Lq), self.dev)
+        L.check(self.lib.dfb_attention_bwd(L.ptr(q), ldq, L.ptr(k), ldk, L.ptr(v), ldv, L.ptr(o), Cc, L.ptr(dO), Cc, B,
+                                           self.heads, Lq, Lk, d, d ** -0.5, L.ptr(dq), lddq, L.ptr(dk), lddk, L.ptr(dv),
+                                           lddv, L.ptr(ws[0]), L.ptr(ws[1]), L.cur_stream()), "dfb_attention_bwd")
+
+    # ---- blocks: forward returns (out32, saved); backward takes (dout32, dout16, saved) -> (dx32, dx16)
+    def res_fwd(self, path, x32, B, H, W, semb16):
+        w = self.w
+        cin, cout, HW = w[path + ".conv1"]["cin"], w[path + ".conv1"]["cout"], H * W
+        a16 = self.gn(x32, cin, B, HW, w[path + ".gn1"], 1e-5, 1)
+        emb, _ = self.gemm(semb16, w[path + ".emb"]["f"], w[path + ".emb"]["bias"])
+        h1, _ = self.conv3(a16.view(B, H, W, cin), w[path + ".conv1"]["f"], B, H, W, w[path + ".conv1"]["bias"], rowvec=emb)
+        b16 = self.gn(h1, cout, B, HW, w[path + ".gn2"], 1e-5, 1)
+        if (path + ".skip") in w:
+            x16 = _e((B * HW, cin), self.dev, torch.float16)
+            L.check(self.lib.dfb_cast_f16(L.ptr(x32), L.ptr(x16), x32.numel(), L.cur_stream()), "dfb_cast_f16")
+            skip, _ = self.gemm(x16, w[path + ".skip"]["f"], w[path + ".skip"]["bias"])
+        else:
+            skip = x32
+        out, _ = self.conv3(b16.view(B, H, W, cout), w[path + ".conv2"]["f"], B, H, W, w[path + ".conv2"]["bias"], residual=skip)
+        return out, (x32, h1, B, H, W)
+
+    def res_bwd(self, path, dout32, dout16, saved):
+        w = self.w
+        x32, h1, B, H, W = saved
+        cin, cout, HW = w[path + ".conv1"]["cin"], w[path + ".conv1"]["cout"], H * W
+        db, _ = self.conv3(dout16.view(B, H, W, cout), w[path + ".conv2"]["b"], B, H, W)
+        _, dh1 = self.gn_bwd(h1, cout, B, HW, w[path + ".gn2"], 1e-5, 1, db, None, o32=False)
+        da, _ = self.conv3(dh1.view(B, H, W, cout), w[path + ".conv1"]["b"], B, H, W)
+        if (path + ".skip") in w:
+            dskip, _ = self.gemm(dout16, w[path + ".skip"]["b"])
+        else:
+            dskip = dout32
+        return self.gn_bwd(x32, cin, B, HW, w[path + ".gn1"], 1e-5, 1, da, dskip)
+
+    def st_fwd(self, path, x32, B, H, W, ctx16, T):
+        w, Lq = self.w, H * W
+        Cc = x32.shape[1]
+        d = Cc // self.heads
+        n16 = self.gn(x32, Cc, B, Lq, w[path + ".gn"], 1e-6, 0)
+        x0, _ = self.gemm(n16, w[path + ".proj_in"]["f"], w[path + ".proj_in"]["bias"])
+        l1 = self.ln(x0, w[path + ".ln1"])
+        _, qkv = self.gemm(l1, w[path + ".qkv"]["f"], o32=False, o16=True)
+        o1 = self.attn(qkv, 3 * Cc, qkv[:, Cc:], 3 * Cc, qkv[:, 2 * Cc:], 3 * Cc, B, Lq, Lq, d)
+        x1, _ = self.gemm(o1, w[path + ".out1"]["f"], w[path + ".out1"]["bias"], residual=x0)
+        l2 = self.ln(x1, w[path + ".ln2"])
+        _, q2 = self.gemm(l2, w[path + ".q2"]["f"], o32=False, o16=True)
+        _, kv = self.gemm(ctx16, w[path + ".kv"]["f"], o32=False, o16=True)
+        o2 = self.attn(q2, Cc, kv, 2 * Cc, kv[:, Cc:], 2 * Cc, B, Lq, T, d)
+        x2, _ = self.gemm(o2, w[path + ".out2"]["f"], w[path + ".out2"]["bias"], residual=x1)
+        l3 = self.ln(x2, w[path + ".ln3"])
+        proj, _ = self.gemm(l3, w[path + ".geglu"]["f"], w[path + ".geglu"]["bias"])
+        F4 = proj.shape[1] // 2
+        h16 = _e((B * Lq, F4), self.dev, torch.float16)
+        L.check(self.lib.dfb_geglu_fwd(L.ptr(proj), B * Lq, F4, L.ptr(h16), L.cur_stream()), "dfb_geglu_fwd")
+        _, x3 = self.gemm(h16, w[path + ".ffout"]["f"], w[path + ".ffout"]["bias"], residual=x2, o32=False, o16=True)
+        out, _ = self.gemm(x3, w[path + ".proj_out"]["f"], w[path + ".proj_out"]["bias"], residual=x32)
+        return out, (x32, x0, x1, x2, qkv, o1, q2, kv, o2, proj, B, H, W, T)
+
+    def st_bwd(self, path, dout32, dout16, saved):
+        w = self.w
+        x32, x0, x1, x2, qkv, o1, q2, kv, o2, proj, B, H, W, T = saved
+        Lq, Cc = H * W, x32.shape[1]
+        d = Cc // self.heads
+        dx3, dx3h = self.gemm(dout16, w[path + ".proj_out"]["b"], o16=True)
+        dh, _ = self.gemm(dx3h, w[path + ".ffout"]["b"])
+        F4 = proj.shape[1] // 2
+        dproj = _e((B * Lq, 2 * F4), self.dev, torch.float16)
+        L.check(self.lib.dfb_geglu_bwd(L.ptr(proj), L.ptr(dh), B * Lq, F4, L.ptr(dproj), L.cur_stream()), "dfb_geglu_bwd")
+        dl3, _ = self.gemm(dproj, w[path + ".geglu"]["b"])
+        dx2, dx2h = self.ln_bwd(x2, w[path + ".ln3"], dl3, dx3)
+        do2, _ = self.gemm(dx2h, w[path + ".out2"]["b"])
+        dq2 = _e((B * Lq, Cc), self.dev, torch.float16)
+        self.attn_bwd(q2, Cc, kv, 2 * Cc, kv[:, Cc:], 2 * Cc, o2, do2, B, Lq, T, d, dq2, Cc)
+        dl2, _ = self.gemm(dq2, w[path + ".q2"]["b"])
+        dx1, dx1h = self.ln_bwd(x1, w[path + ".ln2"], dl2, dx2)
+        do1, _ = self.gemm(dx1h, w[path + ".out1"]["b"])
+        dqkv = _e((B * Lq, 3 * Cc), self.dev, torch.float16)
+        self.attn_bwd(qkv, 3 * Cc, qkv[:, Cc:], 3 * Cc, qkv[:, 2 * Cc:], 3 * Cc, o1, do1, B, Lq, Lq, d, dqkv, 3 * Cc,
+                      dqkv[:, Cc:], 3 * Cc, dqkv[:, 2 * Cc:], 3 * Cc)
+        dl1, _ = self.gemm(dqkv, w[path + ".qkv"]["b"])
+        dx0, dx0h = self.ln_bwd(x0, w[path + ".ln1"], dl1, dx1)
+        dn, _ = self.gemm(dx0h, w[path + ".proj_in"]["b"])
+        return self.gn_bwd(x32, Cc, B, Lq, w[path + ".gn"], 1e-6, 0, dn, dout32)
+
+    def down_fwd(self, path, x32, B, H, W):
+        p = self.w[path]
+        Cc = p["cin"]
+        col = _e((B * (H // 2) * (W // 2), 9 * Cc), self.dev, torch.float16)
+        L.check(self.lib.dfb_im2col_s2(L.ptr(x32), L.ptr(col), B, H, W, Cc, L.cur_stream()), "dfb_im2col_s2")
+        out, _ = self.gemm(col, p["f"], p["bias"])
+        return out, (B, H, W, Cc)
+
+    def down_bwd(self, path, dout16, saved):
+        B, H, W, Cc = saved
+        dcol, _ = self.gemm(dout16, self.w[path]["bt"])
+        d32, d16 = _e((B * H * W, Cc), self.dev), _e((B * H * W, Cc), self.dev, torch.float16)
+        L.check(self.lib.dfb_col2im_s2(L.ptr(dcol), B, H, W, Cc, None, L.ptr(d32), L.ptr(d16), L.cur_stream()), "dfb_col2im_s2")
+        return d32, d16
+
+    @torch.no_grad()
+    def grad(self, x, t, feats, scale, want_grad=True):
+        """x [B,4,H,W] fp32, t [B] int64 / float, feats [B,T,ctx] -> (prob [B], d/dx sum log prob * scale [B,4,H,W])"""
+        m, w, lib, dev = self.m, self.w, self.lib, self.dev
+        B, _, H, W = x.shape
+        x = x.detach().to(dev, torch.float32).contiguous()
+        T = feats.shape[1]
+        ctx16 = feats.detach().to(dev, torch.float32).reshape(B * T, -1).contiguous()
+        c16 = _e(ctx16.shape, dev, torch.float16)
+        L.check(lib.dfb_cast_f16(L.ptr(ctx16), L.ptr(c16), ctx16.numel(), L.cur_stream()), "dfb_cast_f16")
+        tt = t.to(dev)
+        is_f = 1 if tt.dtype.is_floating_point else 0
+        tt = (tt.to(torch.float32) if is_f else tt.to(torch.int64)).contiguous()
+        te = _e((B, m.model_channels), dev, torch.float16)
+        L.check(lib.dfb_temb(L.ptr(tt), is_f, B, m.model_channels, L.ptr(te), L.cur_stream()), "dfb_temb")
+        _, e1 = self.gemm(te, w["time_embed.0"]["f"], w["time_embed.0"]["bias"], act=SILU, o32=False, o16=True)
+        _, semb = self.gemm(e1, w["time_embed.2"]["f"], w["time_embed.2"]["bias"], act=SILU, o32=False, o16=True)
+        # ---- forward
+        h = _e((B * H * W, w["stem"]["cout"]), dev)
+        L.check(lib.dfb_stem_conv(L.ptr(x), B, w["stem"]["cin"], H, W, L.ptr(w["stem"]["f"]), L.ptr(w["stem"]["bias"]),
+                                  w["stem"]["cout"], L.ptr(h), L.cur_stream()), "dfb_stem_conv")
+        tape = []
+        for blk in m._layout:
+            for kind, path in blk:
+                if kind == "stem":
+                    continue
+                if kind == "res":
+                    h, sv = self.res_fwd(path, h, B, H, W, semb)
+                elif kind == "st":
+                    h, sv = self.st_fwd(path, h, B, H, W, c16, T)
+                else:
+                    h, sv = self.down_fwd(path, h, B, H, W)
+                    H, W = H // 2, W // 2
+                tape.append((kind, path, sv))
+        Cl = h.shape[1]
+        a16 = self.gn(h, Cl, B, H * W, w["out.gn"], 1e-5, 1)
+        c, _ = self.conv3(a16.view(B, H, W, Cl), w["out.conv"]["f"], B, H, W, w["out.conv"]["bias"])
+        prob = _e((B,), dev)
+        Cm = c.shape[1]
+        dc = _e((B * H * W, Cm), dev, torch.float16) if want_grad else None
+        L.check(lib.dfb_classifier_head(L.ptr(c), B, H * W, Cm, L.ptr(w["cls"]["w"]), L.ptr(w["cls"]["bias"]),
+                                        float(scale) * LOSS_SCALE, L.ptr(prob), L.ptr(dc), L.cur_stream()), "dfb_classifier_head")
+        if not want_grad:
+            return prob, None
+        # ---- backward
+        dA, _ = self.conv3(dc.view(B, H, W, Cm), w["out.conv"]["b"], B, H, W)
+        d32, d16 = self.gn_bwd(h, Cl, B, H * W, w["out.gn"], 1e-5, 1, dA, None)
+        for kind, path, sv in reversed(tape):
+            if kind == "res":
+                d32, d16 = self.res_bwd(path, d32, d16, sv)
+            elif kind == "st":
+                d32, d16 = self.st_bwd(path, d32, d16, sv)
+            else:
+                d32, d16 = self.down_bwd(path, d16, sv)
+        H0, W0 = x.shape[2], x.shape[3]
+        g = _e(x.shape, dev)
+        L.check(lib.dfb_head_conv(L.ptr(d16), B, H0, W0, w["stem"]["cout"], L.ptr(w["stem"]["b"]), L.ptr(w["stem"]["zb"]),
+                                  w["stem"]["cin"], L.ptr(g), L.cur_stream()), "dfb_head_conv")
+        L.check(lib.dfb_scale_f32(L.ptr(g), 1.0 / LOSS_SCALE, g.numel(), L.cur_stream()), "dfb_scale_f32")
+        return prob, g
+
+
 # Double_Guidance_Classifier.yaml (inference/config): the 11.45 M-parameter half-UNet
 DIFF_FOLEY_CLASSIFIER_PARAMS = dict(image_size=32, in_channels=4, out_channels=1, model_channels=128,
                                     attention_resolutions=[2, 4], num_res_blocks=1, channel_mult=[1, 2, 2],
@@ -165,6 +457,29 @@ class AlignmentClassifierDoubleGuidanceB200(nn.Module):
     def forward(self, spec_noisy, video_feat, t):
         return self.model(spec_noisy, context=video_feat, timesteps=t)
 
+    # ---- the native path the samplers use (ddim.py:333-341 / dpm_solver.py:1340-1350)
+    def _native(self, dev):
+        fp = sum(p._version for p in self.model.parameters())
+        nat = getattr(self, "_nat", None)
+        if nat is None or nat.dev != dev or self._nat_fp != fp:
+            self._nat, self._nat_fp = _Native(self.model, dev), fp
+        return self._nat
+
+    @torch.no_grad()
+    def loglikelihood_grad(self, x, t, video_feat, classifier_guide_scale):
+        """grad_x [ sum log classifier(x, t, video_feat) ] * classifier_guide_scale, on the hand-written kernels."""
+        if not x.is_cuda:
+            raise RuntimeError("the classifier gradient runs on a CUDA (sm_100a) device only; there is no CPU path")
+        with torch.cuda.device(x.device):
+            return self._native(x.device).grad(x, t, video_feat, classifier_guide_scale)[1]
+
+    @torch.no_grad()
+    def probability(self, x, t, video_feat):
+        with torch.cuda.device(x.device):
+            return self._native(x.device).grad(x, t, video_feat, 0.0, want_grad=False)[0].view(-1, 1)
+
     @staticmethod
     def backend_description():
-        return "torch autograd on the GPU (cuDNN / cuBLAS library kernels) -- forward + backward, see classifier.py"
+        return ("hand-written kernels over the C ABI: tcgen05 implicit GEMM for every conv / Linear forward and "
+                "backward-data, csrc/backward.cu for GroupNorm / LayerNorm / attention / GEGLU backward (no autograd, "
+                "no cuDNN / cuBLAS)")

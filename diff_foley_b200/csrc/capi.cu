@@ -163,6 +163,83 @@ int dfb_conv_taps(const void* a, const void* w, int B, int T, int H, int W, int 
 
 void dfb_debug_igemm_force(int bn, int deep) { igemm_force(bn, deep); }
 
+// ---- backward / classifier ops (backward.cu) and the small-channel boundary convs
+int dfb_groupnorm_bwd(const float* x, int C, int B, int HW, const float* gamma, const float* beta, float eps, int silu,
+                      const float* dy, const float* add, float* dx_f32, void* dx_f16, void* stream) {
+  if (!x || !gamma || !beta || !dy || (!dx_f32 && !dx_f16)) { set_error("dfb_groupnorm_bwd: null argument"); return DFB_E_INVALID; }
+  int r = kernels_init();
+  if (r) return r;
+  return groupnorm_bwd_launch(x, C, B, HW, gamma, beta, eps, silu, dy, add, dx_f32, (__half*)dx_f16, (cudaStream_t)stream);
+}
+int dfb_layernorm_bwd(const float* x, int rows, int C, const float* gamma, float eps, const float* dy, const float* add,
+                      float* dx_f32, void* dx_f16, void* stream) {
+  if (!x || !gamma || !dy || (!dx_f32 && !dx_f16)) { set_error("dfb_layernorm_bwd: null argument"); return DFB_E_INVALID; }
+  int r = kernels_init();
+  if (r) return r;
+  return layernorm_bwd_launch(x, rows, C, gamma, eps, dy, add, dx_f32, (__half*)dx_f16, (cudaStream_t)stream);
+}
+int dfb_attention_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* o, int ldo,
+                      const float* dO, int lddo, int B, int heads, int Lq, int Lk, int d, float scale, void* dq, int lddq,
+                      void* dk, int lddk, void* dv, int lddv, float* lse_ws, float* d_ws, void* stream) {
+  if (!q || !k || !v || !o || !dO || !dq || !lse_ws || !d_ws) { set_error("dfb_attention_bwd: null argument"); return DFB_E_INVALID; }
+  int r = kernels_init();
+  if (r) return r;
+  return attention_bwd_launch((const __half*)q, ldq, (const __half*)k, ldk, (const __half*)v, ldv, (const __half*)o, ldo,
+                              dO, lddo, B, heads, Lq, Lk, d, scale, (__half*)dq, lddq, (__half*)dk, lddk, (__half*)dv,
+                              lddv, lse_ws, d_ws, (cudaStream_t)stream);
+}
+int dfb_geglu_fwd(const float* proj, long long M, int F, void* h_f16, void* stream) {
+  if (!proj || !h_f16) { set_error("dfb_geglu_fwd: null argument"); return DFB_E_INVALID; }
+  int r = kernels_init();
+  if (r) return r;
+  return geglu_fwd_launch(proj, (long)M, F, (__half*)h_f16, (cudaStream_t)stream);
+}
+int dfb_geglu_bwd(const float* proj, const float* dh, long long M, int F, void* dproj_f16, void* stream) {
+  if (!proj || !dh || !dproj_f16) { set_error("dfb_geglu_bwd: null argument"); return DFB_E_INVALID; }
+  int r = kernels_init();
+  if (r) return r;
+  return geglu_bwd_launch(proj, dh, (long)M, F, (__half*)dproj_f16, (cudaStream_t)stream);
+}
+int dfb_col2im_s2(const float* dcol, int B, int H, int W, int C, const float* add, float* dx_f32, void* dx_f16, void* stream) {
+  if (!dcol || (!dx_f32 && !dx_f16) || (H & 1) || (W & 1)) { set_error("dfb_col2im_s2: bad argument"); return DFB_E_INVALID; }
+  int r = kernels_init();
+  if (r) return r;
+  return col2im_s2_launch(dcol, B, H, W, C, add, dx_f32, (__half*)dx_f16, (cudaStream_t)stream);
+}
+int dfb_classifier_head(const float* c, int B, int HW, int C, const float* w, const float* bias, float seed_scale,
+                        float* prob, void* dc_f16, void* stream) {
+  if (!c || !w || !bias) { set_error("dfb_classifier_head: null argument"); return DFB_E_INVALID; }
+  int r = kernels_init();
+  if (r) return r;
+  return classifier_head_launch(c, B, HW, C, w, bias, seed_scale, prob, (__half*)dc_f16, (cudaStream_t)stream);
+}
+int dfb_scale_f32(float* x, float s, long long n, void* stream) {
+  if (!x) { set_error("dfb_scale_f32: null argument"); return DFB_E_INVALID; }
+  int r = kernels_init();
+  if (r) return r;
+  return scale_f32_launch(x, s, (long)n, (cudaStream_t)stream);
+}
+int dfb_cast_f16(const float* src, void* dst_f16, long long n, void* stream) {
+  if (!src || !dst_f16) { set_error("dfb_cast_f16: null argument"); return DFB_E_INVALID; }
+  int r = kernels_init();
+  if (r) return r;
+  return cast_f16_launch(src, (__half*)dst_f16, (size_t)n, (cudaStream_t)stream);
+}
+int dfb_stem_conv(const float* x_nchw, int B, int Cin, int H, int W, const float* w_packed, const float* bias, int Cout,
+                  float* out_nhwc, void* stream) {
+  if (!x_nchw || !w_packed || !bias || !out_nhwc) { set_error("dfb_stem_conv: null argument"); return DFB_E_INVALID; }
+  int r = kernels_init();
+  if (r) return r;
+  return stem_conv_launch(x_nchw, B, 0, B, Cin, H, W, w_packed, bias, Cout, out_nhwc, (cudaStream_t)stream);
+}
+int dfb_head_conv(const void* a_f16_nhwc, int B, int H, int W, int C, const float* w_packed, const float* bias, int Cout,
+                  float* out_nchw, void* stream) {
+  if (!a_f16_nhwc || !w_packed || !bias || !out_nchw || Cout > 4) { set_error("dfb_head_conv: bad argument"); return DFB_E_INVALID; }
+  int r = kernels_init();
+  if (r) return r;
+  return head_conv_launch((const __half*)a_f16_nhwc, B, H, W, C, w_packed, bias, Cout, out_nchw, (cudaStream_t)stream);
+}
+
 int dfb_frames_resize(const void* src_u8, int N, int H, int W, int swap_rb, const int32_t* kk_h, const int32_t* bounds_h,
                       int ksize_h, int OW, const int32_t* kk_v, const int32_t* bounds_v, int ksize_v, int OH,
                       void* tmp_u8, float* out_f32, void* out_u8, void* stream) {

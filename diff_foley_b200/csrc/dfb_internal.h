@@ -202,4 +202,21 @@ int ddim_update_launch(const float* x, const float* eps_uncond, const float* eps
                        float sqrt_a_prev, float dir_coef, float grad_coef, float* x_prev,
                        float* pred_x0, size_t n, cudaStream_t stream);
 
+// ------------------------------------------------------------- backward kernels (backward.cu)
+int groupnorm_bwd_launch(const float* x, int C, int B, int HW, const float* gamma, const float* beta, float eps,
+                         int silu, const float* dy, const float* add, float* dx32, __half* dx16, cudaStream_t stream);
+int layernorm_bwd_launch(const float* x, int rows, int C, const float* gamma, float eps, const float* dy,
+                         const float* add, float* dx32, __half* dx16, cudaStream_t stream);
+int attention_bwd_launch(const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, const __half* o,
+                         int ldo, const float* dO, int lddo, int B, int heads, int Lq, int Lk, int d, float scale,
+                         __half* dq, int lddq, __half* dk, int lddk, __half* dv, int lddv, float* lse_ws, float* d_ws,
+                         cudaStream_t stream);
+int geglu_fwd_launch(const float* proj, long M, int F, __half* h, cudaStream_t stream);
+int geglu_bwd_launch(const float* proj, const float* dh, long M, int F, __half* dproj, cudaStream_t stream);
+int col2im_s2_launch(const float* dcol, int B, int H, int W, int C, const float* add, float* dx32, __half* dx16,
+                     cudaStream_t stream);
+int classifier_head_launch(const float* c, int B, int HW, int C, const float* w, const float* bias, float seed_scale,
+                           float* prob, __half* dc, cudaStream_t stream);
+int scale_f32_launch(float* x, float s, long n, cudaStream_t stream);
+
 }  // namespace dfb

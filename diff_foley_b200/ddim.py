@@ -136,12 +136,15 @@ class DDIMSamplerB200(object):
             else:
                 e_u, e_c = None, self.model.apply_model(img, ts, conditioning).to(torch.float32).contiguous()
             grad = None
-            if classifier is not None:  # ddim.py:333-341 -- stays on torch autograd
-                with torch.enable_grad():
-                    x_in = img.detach().requires_grad_(True)
-                    log_probs = torch.log(classifier(x_in, t=ts, video_feat=origin_cond))
-                    grad = (torch.autograd.grad(log_probs.sum(), x_in)[0] * classifier_guide_scale)
-                    grad = grad.to(torch.float32).contiguous()
+            if classifier is not None:  # ddim.py:333-341
+                if hasattr(classifier, "loglikelihood_grad"):      # native forward + backward (classifier.py)
+                    grad = classifier.loglikelihood_grad(img, ts, origin_cond, classifier_guide_scale)
+                else:                                              # a foreign classifier module: its own autograd
+                    with torch.enable_grad():
+                        x_in = img.detach().requires_grad_(True)
+                        log_probs = torch.log(classifier(x_in, t=ts, video_feat=origin_cond))
+                        grad = (torch.autograd.grad(log_probs.sum(), x_in)[0] * classifier_guide_scale)
+                grad = grad.to(torch.float32).contiguous()
             nxt = torch.empty_like(img)
             with torch.cuda.device(device):
                 L.check(lib.dfb_ddim_step(

@@ -145,9 +145,12 @@ class DPMSolverSamplerB200(object):
                 e_u, e_c = e.chunk(2)
                 noise = e_u + scale * (e_c - e_u)
                 if classifier is not None:
-                    with torch.enable_grad():
-                        x_in = x.detach().requires_grad_(True)
-                        grad = torch.autograd.grad(torch.log(classifier(x_in, t=t_in, video_feat=origin_cond)).sum(), x_in)[0]
+                    if hasattr(classifier, "loglikelihood_grad"):
+                        grad = classifier.loglikelihood_grad(x, t_in, origin_cond, 1.0)
+                    else:
+                        with torch.enable_grad():
+                            x_in = x.detach().requires_grad_(True)
+                            grad = torch.autograd.grad(torch.log(classifier(x_in, t=t_in, video_feat=origin_cond)).sum(), x_in)[0]
                     noise = noise - cscale * f(sch["sigma"][k]) * grad
             else:
                 noise = self.model.apply_model(x, t_in, cond).float()

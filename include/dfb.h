@@ -104,6 +104,39 @@ int dfb_dpm_solver_sample(dfb_handle h, float* x_dev, const float* cond_dev, con
                           int n_clips, int ctx_len, float cfg_scale, int n_evals, const float* t_input,
                           const float* sigma, const float* alpha, const float* cx, const float* a_coef,
                           const float* inv_r0, const int32_t* order, float* pred_x0_dev, void* stream);
+/* ---- backward ops of the double-guidance classifier gradient (ddim.py:333-341 through Classifier_Backbone,
+ * alignment_backbone.py:417-686).  Backward-data of convs / Linears are dfb_conv3x3 / dfb_gemm with rotated /
+ * transposed weights; these are the remaining pieces.  fp32 channels-last activations [B,HW,C]; `add` (optional
+ * fp32) is summed into dx (residual branch); dx is written as fp32 and/or fp16 (either may be NULL). */
+int dfb_groupnorm_bwd(const float* x_dev, int C, int B, int HW, const float* gamma_dev, const float* beta_dev,
+                      float eps, int silu, const float* dy_dev, const float* add_dev, float* dx_f32_dev,
+                      void* dx_f16_dev, void* stream);
+int dfb_layernorm_bwd(const float* x_dev, int rows, int C, const float* gamma_dev, float eps, const float* dy_dev,
+                      const float* add_dev, float* dx_f32_dev, void* dx_f16_dev, void* stream);
+/* softmax(q k^T scale) v backward per (sample, head), d <= 64: q/k/v/o fp16 (head h at columns h*d), dO fp32;
+ * dq/dk/dv fp16 (dk, dv may be NULL: cross-attention against a constant context); lse_ws / d_ws: fp32
+ * [B*heads*Lq] scratch.  Deterministic (no atomics). */
+int dfb_attention_bwd(const void* q_dev, int ldq, const void* k_dev, int ldk, const void* v_dev, int ldv,
+                      const void* o_dev, int ldo, const float* dO_dev, int lddo, int B, int heads, int Lq, int Lk,
+                      int d, float scale, void* dq_dev, int lddq, void* dk_dev, int lddk, void* dv_dev, int lddv,
+                      float* lse_ws_dev, float* d_ws_dev, void* stream);
+/* GEGLU on an un-interleaved projection fp32 [M, 2F] = [value | gate] (attention_openai.py:37-44) */
+int dfb_geglu_fwd(const float* proj_dev, long long M, int F, void* h_f16_dev, void* stream);
+int dfb_geglu_bwd(const float* proj_dev, const float* dh_dev, long long M, int F, void* dproj_f16_dev, void* stream);
+/* backward-data scatter of the 3x3 / stride-2 Downsample conv as a gather: dcol fp32 [B*(H/2)*(W/2), 9*C] */
+int dfb_col2im_s2(const float* dcol_dev, int B, int H, int W, int C, const float* add_dev, float* dx_f32_dev,
+                  void* dx_f16_dev, void* stream);
+/* avg-pool + Linear(C -> 1) + sigmoid (alignment_backbone.py:676-686) and the seed of d log(prob) / dc * seed_scale */
+int dfb_classifier_head(const float* c_dev, int B, int HW, int C, const float* w_dev, const float* bias_dev,
+                        float seed_scale, float* prob_dev, void* dc_f16_dev, void* stream);
+int dfb_scale_f32(float* x_dev, float s, long long n, void* stream);
+int dfb_cast_f16(const float* src_dev, void* dst_f16_dev, long long n, void* stream);
+/* the 4-channel boundary convs: stem (NCHW fp32 -> NHWC fp32, w packed [(ci*9+tap), Cout]) and head (NHWC fp16 ->
+ * NCHW fp32, Cout <= 4, w packed [Cout, 9, C]); 3x3, pad 1 */
+int dfb_stem_conv(const float* x_nchw_dev, int B, int Cin, int H, int W, const float* w_packed_dev,
+                  const float* bias_dev, int Cout, float* out_nhwc_dev, void* stream);
+int dfb_head_conv(const void* a_f16_nhwc_dev, int B, int H, int W, int C, const float* w_packed_dev,
+                  const float* bias_dev, int Cout, float* out_nchw_dev, void* stream);
 /* CAVP frame ingest (reference inference/demo_util.py:135-163: cv2 BGR->RGB, PIL Resize((224,224)), ToTensor).
  * src: N uint8 frames [N,H,W,3] on the device (swap_rb = 1 for cv2's BGR order).  kk_* / bounds_* are the
  * int32 coefficient tables of Pillow's resample for (W -> OW) and (H -> OH) (precompute_coeffs +
