@@ -75,6 +75,7 @@ SIGNATURES = {
     "dfb_unet_profile": (_i, [_vp, _fp, _i, _vp, _i, _fp, _i, _i, C.POINTER(OpInfo), _i, C.POINTER(_i), _vp]),
     "dfb_unet_trace": (_i, [_vp, _fp, _i, _vp, _i, _fp, _i, C.POINTER(C.c_ulonglong), _i, C.POINTER(_i), _vp]),
     "dfb_debug_igemm_force": (None, [_i, _i]),
+    "dfb_debug_igemm_pair": (None, [_i]),
     "dfb_unet_debug_num_taps": (_i, [_vp, _i]),
     "dfb_unet_debug_tap": (_i, [_vp, _i, _i, C.c_char_p, _i, C.POINTER(C.c_int32), _fp, _vp]),
     "dfb_unet_last_launch_count": (C.c_longlong, [_vp]),

@@ -162,6 +162,7 @@ int dfb_conv_taps(const void* a, const void* w, int B, int T, int H, int W, int 
 }
 
 void dfb_debug_igemm_force(int bn, int deep) { igemm_force(bn, deep); }
+void dfb_debug_igemm_pair(int pair) { igemm_force_pair(pair); }
 
 // ---- backward / classifier ops (backward.cu) and the small-channel boundary convs
 int dfb_groupnorm_bwd(const float* x, int C, int B, int HW, const float* gamma, const float* beta, float eps, int silu,

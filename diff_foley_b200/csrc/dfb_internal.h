@@ -129,6 +129,7 @@ struct IGemmPlan {
   int BN;            // tile N (64 or 128)
   int tiles_m, tiles_n, splits;  // splits == cluster size along grid.z
   int deep = -1;     // operand ring: 1 = deep (1 CTA/SM), 0 = shallow (2 CTAs/SM), -1 = launcher's default
+  int pair = 0;      // 1 = CTA-pair tiles (tcgen05.mma.cta_group::2, 256 x BN per SM pair), no split-K
   // weights of the NEXT GEMM of the plan: every CTA issues an L2 prefetch for a slice of them, so the
   // next (weight-streaming) kernel finds its operand in L2 instead of waiting on cold HBM misses
   const void* next_w = nullptr;
@@ -144,6 +145,8 @@ int igemm_launch(const IGemmPlan& plan, cudaStream_t stream);
 // tuning aid (tools/autotune_igemm.py): force the tile width (64 / 128, 0 = planner's choice) and the
 // ring depth (1 / 0, -1 = default) of every plan built afterwards
 void igemm_force(int bn, int deep);
+// CTA-pair (cta_group::2) tiles for every plan built afterwards that can take them: 1 on, 0 off, -1 = DFB_PAIR env
+void igemm_force_pair(int pair);
 // geometry for a "same"-padded stride-1 conv with a (kt,kh,kw) kernel over [B,T,H,W,C] (kt*kh*kw <= 9)
 IGemmGeom conv_taps_geom(int B, int T, int H, int W, int C, int kt, int kh, int kw);
 // convenience geometry for a plain [M,K] x [N,K]^T GEMM

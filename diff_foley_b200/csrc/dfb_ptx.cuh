@@ -153,6 +153,62 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
       : "memory");
 }
 
+// ---- cta_group::2 (two CTAs of a cluster = one SM pair share one MMA: M = 256 rows, each CTA holds its 128 rows of A
+// and half of the B tile; accumulators land in both CTAs' TMEM).  PTX forms as CUTLASS issues them
+// (cute/arch/{tmem_allocator,copy_sm100_tma,mma_sm100_umma}.hpp, cutlass/arch/barrier.h).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_slot, uint32_t ncols) {   // one warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {   // issued by the leader CTA only
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once the leader's previously issued MMAs completed) on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit2_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+constexpr uint32_t PAIR_LEADER_MASK = 0xFEFFFFFFu;   // clears the peer bit of a shared::cluster address -> the even CTA
+constexpr uint64_t TMA_EVICT_NORMAL = 0x1000000000000000ull;
+// TMA loads of a CTA pair: the bytes are counted on the LEADER CTA's mbarrier (`leader_bar` = address & PAIR_LEADER_MASK)
+__device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, "
+      "%4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "l"(TMA_EVICT_NORMAL)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_cg2(void* dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1, int c2,
+                                                int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, "
+      "%4, %5, %6, %7}], [%2], %8;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4),
+      "l"(TMA_EVICT_NORMAL)
+      : "memory");
+}
+
 // ------------------------------------------------------------------- UMMA descriptors (sm_100)
 // Shared-memory matrix descriptor, K-major operand tile stored as rows of 64 fp16 (128 B) with the
 // 128-byte swizzle TMA applies (CU_TENSOR_MAP_SWIZZLE_128B): 8-row groups are 1024 B apart (SBO),

@@ -169,6 +169,10 @@ int dfb_unet_profile(dfb_handle h, const float* x_dev, int x_repeat, const void*
 /* Tuning aid (tools/autotune_igemm.py): force the GEMM tile width (64 / 128; 0 = planner's choice) and
  * operand-ring depth (1 deep / 0 shallow; -1 = default) of every GEMM planned afterwards. */
 void dfb_debug_igemm_force(int bn, int deep);
+/* CTA-pair tiles (tcgen05.mma.cta_group::2, 256 x 128 per SM pair) for every GEMM planned afterwards that can take
+ * them (>= 2 M tiles, N >= 128, no split-K): 1 on, 0 off, -1 = follow the DFB_PAIR environment variable (default off:
+ * measured +3-5 % on the large-K convolutions at B_eff = 16, -5-15 % on the short-K Linears) */
+void dfb_debug_igemm_pair(int pair);
 /* In-kernel timeline of one graph-replayed UNet forward (diagnostics): for launch i and mark k,
  * marks[32*i + 2*k] is the first and ~marks[32*i + 2*k + 1] the last %globaltimer reading (ns) at
  * which a CTA of that launch passed the mark; mark 0 = kernel entry, 1 = programmatic-dependent-

@@ -430,3 +430,34 @@ def test_groupnorm_large_batch():
     sync()
     ref = F.silu(F.group_norm(x.permute(0, 2, 1), 32, gamma, beta, 1e-5)).permute(0, 2, 1)
     assert rel_l2(out.float(), ref) < 1e-3
+
+
+@pytest.mark.parametrize("M,N,K,act", [(512, 256, 128, 0), (2048, 320, 320, 0), (300, 128, 64, 0), (4096, 640, 640, 0),
+                                       (1024, 2560, 320, 2), (1152, 384, 1600, 0)])
+def test_gemm_cta_pair_mode(M, N, K, act):
+    """tcgen05.mma.cta_group::2: two CTAs of a cluster share one 256 x 128 tile (each loads its 128 rows of A and half
+    of the weight tile, both CTAs' TMA loads count on the leader's barrier, the commits are multicast).  Same result
+    as the single-CTA kernel, bit for bit (identical K order and epilogue); odd M-tile counts leave the last pair's
+    second CTA without rows."""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(DEV).half()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV).half()
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV) if act == 0 else None
+    outs = []
+    try:
+        for pair in (0, 1):
+            L.lib().dfb_debug_igemm_pair(pair)
+            o32 = torch.full((M, N), float("nan"), device=DEV) if act == 0 else None
+            o16 = torch.full((M, N // 2), float("nan"), device=DEV, dtype=torch.float16) if act == 2 else None
+            L.check(L.lib().dfb_gemm(L.ptr(a), L.ptr(w), M, N, K, L.ptr(bias), L.ptr(res), act, L.ptr(o32), L.ptr(o16), 1,
+                                     L.cur_stream()), "dfb_gemm")
+            sync()
+            outs.append(o32 if act == 0 else o16)
+    finally:
+        L.lib().dfb_debug_igemm_pair(-1)
+    assert torch.isfinite(outs[1].float()).all()
+    if act == 0:
+        ref = a.float() @ w.float().t() + bias + res
+        assert rel_l2(outs[1], ref) < 3e-6
+    assert torch.equal(outs[0], outs[1])
