@@ -19,6 +19,7 @@ the oracle) is not on the sampling path.
 import math
 
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -467,11 +468,39 @@ class AlignmentClassifierDoubleGuidanceB200(nn.Module):
 
     @torch.no_grad()
     def loglikelihood_grad(self, x, t, video_feat, classifier_guide_scale):
-        """grad_x [ sum log classifier(x, t, video_feat) ] * classifier_guide_scale, on the hand-written kernels."""
+        """grad_x [ sum log classifier(x, t, video_feat) ] * classifier_guide_scale, on the hand-written kernels.
+        The ~190 launches of one forward + backward are captured once per (shapes, scale) as a CUDA graph over
+        static input / output buffers and replayed (the sampler calls this every step with the same shapes)."""
         if not x.is_cuda:
             raise RuntimeError("the classifier gradient runs on a CUDA (sm_100a) device only; there is no CPU path")
-        with torch.cuda.device(x.device):
-            return self._native(x.device).grad(x, t, video_feat, classifier_guide_scale)[1]
+        dev = x.device
+        with torch.cuda.device(dev):
+            nat = self._native(dev)
+            if os.environ.get("DFB_NO_CLF_GRAPH"):
+                return nat.grad(x, t, video_feat, classifier_guide_scale)[1]
+            key = (tuple(x.shape), tuple(video_feat.shape), t.dtype.is_floating_point, float(classifier_guide_scale), id(nat))
+            ent = getattr(self, "_graphs", {}).get(key)
+            if ent is None:
+                sx = x.detach().float().clone()
+                st = (t.detach().float() if t.dtype.is_floating_point else t.detach().long()).clone()
+                sf = video_feat.detach().float().clone()
+                nat.grad(sx, st, sf, classifier_guide_scale)          # warm-up: one-time kernel attribute setup
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(graph, stream=side):
+                        out = nat.grad(sx, st, sf, classifier_guide_scale)[1]
+                torch.cuda.current_stream(dev).wait_stream(side)
+                ent = (graph, sx, st, sf, out)
+                self.__dict__.setdefault("_graphs", {})[key] = ent
+            graph, sx, st, sf, out = ent
+            sx.copy_(x)
+            st.copy_(t)
+            sf.copy_(video_feat)
+            graph.replay()
+            return out.clone()
 
     @torch.no_grad()
     def probability(self, x, t, video_feat):
