@@ -28,6 +28,7 @@
 // the even 16-key chunks of a block, warps 6..9 the odd ones; the two threads of a row exchange their
 // partial row maxima through shared memory (one 64-thread named barrier per block), keep separate
 // partial row sums, and split the O columns for the rescale and the final normalisation.
+#include <algorithm>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -43,6 +44,7 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 
 constexpr int ATT_THREADS = 320;  // 1 TMA + 1 MMA warp + 2 x 4 softmax warps
 constexpr int ATT_BM = 128;  // queries per CTA
+constexpr int ATT_POLY_DEFAULT = 0;
 
 struct AttParams {
   __half* out;
@@ -93,7 +95,8 @@ __host__ __device__ inline AttSmem att_smem_layout(int dpad, int KB, int kvs) {
 // 256 TMEM columns): one CTA's softmax overlaps the other's tensor-core work and loads.
 // NQ = 16-column chunks of S per key block: 4 (KB <= 64; 2 CTAs/SM -- grids larger than the machine) or
 // 8 (KB <= 128; half as many softmax/MMA round trips per CTA -- small grids, latency-bound).
-template <int NQ>
+// POLY = how many of every four exponentials are evaluated by ex2_poly on the FMA pipe instead of MUFU.EX2
+template <int NQ, int POLY>
 __global__ void __launch_bounds__(ATT_THREADS, (NQ <= 4) ? 2 : 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttParams p) {
@@ -282,7 +285,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           if (full) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              e[i] = ex2_approx(fmaf(__uint_as_float(raw[q][i]), sl, neg_m));
+              const float xs = fmaf(__uint_as_float(raw[q][i]), sl, neg_m);
+              e[i] = ((i & 3) < POLY) ? ex2_poly(xs) : ex2_approx(xs);
               ps4[i & 3] += e[i];
             }
           } else {
@@ -355,10 +359,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 }
 
 int attention_init() {
-  DFB_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   200 * 1024));
-  DFB_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   200 * 1024));
+#define DFB_ATT_ATTR(NQ, PL)                                                                                    \
+  DFB_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<NQ, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   200 * 1024))
+  DFB_ATT_ATTR(4, 0); DFB_ATT_ATTR(4, 1); DFB_ATT_ATTR(4, 2);
+  DFB_ATT_ATTR(8, 0); DFB_ATT_ATTR(8, 1); DFB_ATT_ATTR(8, 2);
+#undef DFB_ATT_ATTR
   return 0;
 }
 
@@ -433,10 +439,17 @@ int attention_launch(const __half* q, int ldq, const __half* k, int ldk, const _
   dim3 grid((Lq + ATT_BM - 1) / ATT_BM, B * heads);
   note("attention", 4.0 * B * heads * (double)Lq * Lk * d,
        2.0 * B * heads * ((double)Lq * d * 2 + (double)Lk * d * 2), Lq, Lk, d, 1, grid.x * grid.y);
-  if (nq == 8)
-    DFB_CUDA_OK(launch_pdl(attention_tcgen05_kernel<8>, dim3(grid), dim3(ATT_THREADS), L.total + 128, stream, tq, tk, tv, p));
-  else
-    DFB_CUDA_OK(launch_pdl(attention_tcgen05_kernel<4>, dim3(grid), dim3(ATT_THREADS), L.total + 128, stream, tq, tk, tv, p));
+  // share of the exponentials moved from MUFU to the FMA pipe (quarters); DFB_ATT_POLY=0|1|2 overrides
+  static const int poly_env = getenv("DFB_ATT_POLY") ? atoi(getenv("DFB_ATT_POLY")) : -1;
+  const int poly = poly_env >= 0 ? std::min(poly_env, 2) : ATT_POLY_DEFAULT;
+#define DFB_ATT_LAUNCH(NQ, PL) \
+  DFB_CUDA_OK(launch_pdl(attention_tcgen05_kernel<NQ, PL>, dim3(grid), dim3(ATT_THREADS), L.total + 128, stream, tq, tk, tv, p))
+  if (nq == 8) {
+    if (poly == 0) DFB_ATT_LAUNCH(8, 0); else if (poly == 1) DFB_ATT_LAUNCH(8, 1); else DFB_ATT_LAUNCH(8, 2);
+  } else {
+    if (poly == 0) DFB_ATT_LAUNCH(4, 0); else if (poly == 1) DFB_ATT_LAUNCH(4, 1); else DFB_ATT_LAUNCH(4, 2);
+  }
+#undef DFB_ATT_LAUNCH
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
 }

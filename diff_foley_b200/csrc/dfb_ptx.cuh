@@ -337,6 +337,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for x <= 0 on the FMA / ALU pipes (no MUFU): Cody-Waite split x = j + f, f in [-0.5, 0.5], cubic minimax
+// 2^f (max relative error 7.7e-5, below the fp16 rounding of the value it feeds), j added into the exponent
+// field.  The softmax of the fused attention kernel is bound by the MUFU pipe at small head dims (one ex2 per
+// 96 MACs at d = 40): a fraction of the exponentials is moved here.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;                  // 1.5 * 2^23: the low mantissa bits of t hold round(x)
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(0.05508868396f, f, 0.24260404706f);
+  p = fmaf(p, f, 0.69327622652f);
+  p = fmaf(p, f, 0.99992895126f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   uint32_t u;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(hi), "f"(lo));
