@@ -258,9 +258,37 @@ class AutoencoderKLDecoderB200(nn.Module):
     @torch.no_grad()
     def decode(self, z):
         """`AutoencoderKL.decode` (autoencoder.py:330-333): z [B,E,h,w] (already divided by the scale
-        factor) -> image [B,out_ch,8h,8w] fp32."""
+        factor) -> image [B,out_ch,8h,8w] fp32.  The ~110 launches of one decode are captured once per latent
+        shape as a CUDA graph over a static input buffer and replayed (DFB_NO_VAE_GRAPH=1: eager)."""
         if not z.is_cuda:
             raise RuntimeError("AutoencoderKLDecoderB200 runs on a B200 only: there is no CPU path")
+        import os
+        if os.environ.get("DFB_NO_VAE_GRAPH"):
+            return self._decode_eager(z)
+        dev = z.device
+        packed = self._pack(dev)
+        key = (tuple(z.shape), str(dev), id(packed))
+        ent = self.__dict__.setdefault("_graphs", {}).get(key)
+        if ent is None:
+            with torch.cuda.device(dev):
+                sz = z.detach().float().clone()
+                self._decode_eager(sz)                    # warm-up: lazy workspaces / kernel attributes
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(graph, stream=side):
+                        out = self._decode_eager(sz)
+                torch.cuda.current_stream(dev).wait_stream(side)
+            ent = self._graphs[key] = (graph, sz, out)
+        graph, sz, out = ent
+        sz.copy_(z)
+        graph.replay()
+        return out.clone()
+
+    @torch.no_grad()
+    def _decode_eager(self, z):
         P = self._pack(z.device)
         B, E, H, W = z.shape
         with torch.cuda.device(z.device):
