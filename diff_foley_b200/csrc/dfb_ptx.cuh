@@ -13,6 +13,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a CONVERGED warp.  Single-thread roles (TMA producer, MMA issuer) must be entered through this, not
+// through `lane == 0`: the compiler then knows exactly one thread runs the branch and keeps the whole loop on the
+// uniform datapath -- with a lane compare it wraps every TMA / MMA / commit instruction in an ELECT ... BRA.U.ANY
+// loop fed by R2UR moves, which made the issuing thread (not the tensor core or the copy engine) the bound of
+// the main loop: ~330 clocks of bookkeeping per k-block (measured).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -461,3 +461,69 @@ def test_gemm_cta_pair_mode(M, N, K, act):
         ref = a.float() @ w.float().t() + bias + res
         assert rel_l2(outs[1], ref) < 3e-6
     assert torch.equal(outs[0], outs[1])
+
+
+# the weight-streaming layers (M <= 32: three quarters or more of the tile rows lie outside the tensor and may not leak
+# into a sum, an exchange or a store): M = 2 (embedding Linears), a ragged M, the level-3 conv with the fused
+# skip, and the GEGLU epilogue, with the 128-wide tile and deep ring the planner gives them
+@pytest.mark.parametrize("M", [2, 17, 32])
+@pytest.mark.parametrize("splits", [1, 3, 8])
+def test_gemm_small_m_box(M, splits):
+    N, K = 1280, 3840
+    g = torch.Generator(device="cpu").manual_seed(M * 31 + splits)
+    a = torch.randn(M, K, generator=g).to(DEV).half()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV).half()
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV)
+    ref = a.float() @ w.float().t() + bias + res
+    lib = L.lib()
+    try:
+        lib.dfb_debug_igemm_force(128, 1)
+        out = gemm(a, w, bias=bias, residual=res, splits=splits)
+        again = gemm(a, w, bias=bias, residual=res, splits=splits)
+    finally:
+        lib.dfb_debug_igemm_force(0, -1)
+    assert torch.isfinite(out).all()
+    assert rel_l2(out, ref) < 4e-6, rel_l2(out, ref)   # (few elements at M = 2: a noisier statistic than the big shapes)
+    assert torch.equal(out, again)
+
+
+def test_gemm_small_m_box_geglu():
+    g = torch.Generator(device="cpu").manual_seed(11)
+    M, C = 32, 1280
+    a = torch.randn(M, C, generator=g).to(DEV).half()
+    w = (torch.randn(8 * C, C, generator=g) / math.sqrt(C)).to(DEV).half()
+    bias = torch.randn(8 * C, generator=g).to(DEV)
+    x, gate = (a.float() @ w.float().t() + bias).chunk(2, dim=-1)
+    ref = x * F.gelu(gate)
+    C4 = 4 * C
+    wi = torch.cat([w[:C4].view(C4 // 64, 64, C), w[C4:].view(C4 // 64, 64, C)], dim=1).reshape(8 * C, C).contiguous()
+    bi = torch.cat([bias[:C4].view(-1, 64), bias[C4:].view(-1, 64)], dim=1).reshape(-1).contiguous()
+    out = gemm(a, wi, bias=bi, act=2, out_dtype=torch.float16, splits=1)
+    assert rel_l2(out.float(), ref) < 1e-3
+
+
+@pytest.mark.parametrize("B,splits", [(2, 0), (2, 5), (1, 8)])
+def test_conv3x3_small_m_box_with_skip(B, splits):
+    H, W, C, C2, N = 2, 8, 1280, 1280, 1280
+    g = torch.Generator(device="cpu").manual_seed(B + splits)
+    a = torch.randn(B, H, W, C, generator=g).to(DEV).half()
+    a2 = torch.randn(B, H, W, C2, generator=g).to(DEV).half()
+    w = (torch.randn(N, C, 3, 3, generator=g) / math.sqrt(9 * C)).to(DEV).half()
+    w2 = (torch.randn(N, C2, generator=g) / math.sqrt(C2)).to(DEV).half()
+    b1 = torch.randn(N, generator=g).to(DEV)
+    b2 = torch.randn(N, generator=g).to(DEV)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = F.conv2d(a.float().permute(0, 3, 1, 2), w.float(), b1, padding=1).permute(0, 2, 3, 1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    ref = ref + a2.float() @ w2.float().t() + b2
+    wp = torch.cat([w.permute(0, 2, 3, 1).reshape(N, 9 * C), w2], dim=1).contiguous()
+    out = torch.full((B, H, W, N), float("nan"), device=DEV, dtype=torch.float32)
+    L.check(L.lib().dfb_conv3x3_cat(L.ptr(a), L.ptr(a2), C2, L.ptr(wp), B, H, W, C, N, L.ptr(b1), L.ptr(b2), None,
+                                    L.ptr(out), None, splits, L.cur_stream()), "dfb_conv3x3_cat")
+    sync()
+    assert torch.isfinite(out).all()
+    assert rel_l2(out, ref) < 3e-6
