@@ -130,6 +130,7 @@ struct IGemmPlan {
   int tiles_m, tiles_n, splits;  // splits == cluster size along grid.z
   int deep = -1;     // operand ring: 1 = deep (1 CTA/SM), 0 = shallow (2 CTAs/SM), -1 = launcher's default
   int pair = 0;      // 1 = CTA-pair tiles (tcgen05.mma.cta_group::2, 256 x BN per SM pair), no split-K
+  int a32 = 0;       // 1 = 32-row activation box + 9-stage ring (<= 32 output positions, weight streaming)
   // weights of the NEXT GEMM of the plan: every CTA issues an L2 prefetch for a slice of them, so the
   // next (weight-streaming) kernel finds its operand in L2 instead of waiting on cold HBM misses
   const void* next_w = nullptr;
