@@ -122,11 +122,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const int nb = p.nblocks;
   const int KB = p.KB;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
   }
   if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_init(q_full, 1);
       for (int i = 0; i < KVS; ++i) {
         mbar_init(&kv_full[i], 1);
@@ -156,21 +156,24 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 
   if (warp == 0) {
     // ======================================================================== TMA producer
-    if (lane == 0) {
+    // (single-thread roles are entered through elect_one(), see dfb_ptx.cuh: the loop stays on the uniform datapath)
+    if (elect_one()) {
+      int st = 0;
+      uint32_t eph = 1;
       // one 2-D box (8 halves x rows) per 16-byte chunk: chunk c lands at tile + c*rows*16
       const int nch = p.dpad >> 3, col0 = h * p.dpad;
       mbar_expect_tx(q_full, L.q_bytes);
       for (int c = 0; c < nch; ++c)
         tma_load_2d(smem + L.off_q + c * (ATT_BM * 16), &tmQ, q_full, col0 + 8 * c, b * p.Lq + q0);
       for (int j = 0; j < nb; ++j) {
-        const int st = j % KVS;
-        mbar_wait(&kv_empty[st], ((j / KVS) & 1) ^ 1);
+        mbar_wait(&kv_empty[st], eph);
         mbar_expect_tx(&kv_full[st], 2 * L.kv_tile_bytes);
         uint8_t* kt = smem + L.off_kv + st * 2 * L.kv_tile_bytes;
         for (int c = 0; c < nch; ++c) {
           tma_load_2d(kt + c * (KB * 16), &tmK, &kv_full[st], col0 + 8 * c, b * p.Lk + j * KB);
           tma_load_2d(kt + L.kv_tile_bytes + c * (KB * 16), &tmV, &kv_full[st], col0 + 8 * c, b * p.Lk + j * KB);
         }
+        if (++st == KVS) { st = 0; eph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -191,11 +194,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                     idesc_s, k > 0 ? 1u : 0u);
       umma_commit(&s_full[s]);
     };
+    if (elect_one()) {
     mbar_wait(q_full, 0);
     mbar_wait(&kv_full[0], 0);
     tc_fence_after();
-    if (lane == 0) issue_s(0);
-    __syncwarp();
+    issue_s(0);
     for (int j = 0; j < nb; ++j) {
       const int s = j & 1;
       if (j + 1 < nb) {
@@ -204,12 +207,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         // S buffer s1 was last read by the softmax of block j-1 (done once P_{j-1} is full)
         if (j >= 1) mbar_wait(&p_full[s1], ((j - 1) >> 1) & 1);
         tc_fence_after();
-        if (lane == 0) issue_s(j + 1);
-        __syncwarp();
+        issue_s(j + 1);
       }
       mbar_wait(&p_full[s], (j >> 1) & 1);
       tc_fence_after();
-      if (lane == 0) {
+      {
         const uint32_t sp = smem_u32(smem + L.off_p + s * L.p_bytes);
         const uint32_t sv = smem_u32(smem + L.off_kv + (j % KVS) * 2 * L.kv_tile_bytes + L.kv_tile_bytes);
 #pragma unroll 1
@@ -220,8 +222,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         umma_commit(pv_done);
         umma_commit(&kv_empty[j % KVS]);
       }
-      __syncwarp();
     }
+    }
+    __syncwarp();
   } else {
     // ============================================================ softmax / correction / epilogue
     const int sub = warp & 3;
