@@ -9,12 +9,7 @@
 #include "dfb_ptx.cuh"
 using namespace dfb;
 
-// whole-warp (uniform control flow) forms: one elected lane issues
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
-  return pred != 0;
-}
+// whole-warp (uniform control flow) forms: one elected lane issues (elect_one() is dfb_ptx.cuh's)
 __device__ __forceinline__ void MMA(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   if (elect_one()) umma_f16_ss(d, a, b, idesc, acc);
 }
