@@ -126,7 +126,8 @@ struct IGemmPlan {
   IGemmGeom g;
   IGemmEpilogue e;
   int M, N, K;       // logical sizes: M = B*T*H*W, K = ntaps*C
-  int BN;            // tile N (64 or 128)
+  int BN;            // tile N: 64, 128, or 256 = the wide variant (bn_run columns of it computed)
+  int bn_run = 0;    // columns per tile actually computed (== BN unless BN == 256)
   int tiles_m, tiles_n, splits;  // splits == cluster size along grid.z
   int deep = -1;     // operand ring: 1 = deep (1 CTA/SM), 0 = shallow (2 CTAs/SM), -1 = launcher's default
   int pair = 0;      // 1 = CTA-pair tiles (tcgen05.mma.cta_group::2, 256 x BN per SM pair), no split-K

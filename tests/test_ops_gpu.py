@@ -527,3 +527,62 @@ def test_conv3x3_small_m_box_with_skip(B, splits):
     sync()
     assert torch.isfinite(out).all()
     assert rel_l2(out, ref) < 3e-6
+
+
+# wide tiles (128 x bn_run, bn_run = any multiple of 16 up to 256, chosen so that the tiles cover N without padding):
+# the large-M variant.  Plain / residual / SiLU / fp16 epilogues, N that is not a multiple of the tile, ragged M,
+# the 3x3 conv with per-sample vector, and the LayerNorm-fold producer + consumer pair (statistics of the two
+# column halves of a tile are merged by the thread that owns the row)
+@pytest.mark.parametrize("M,N,K", [(2048, 320, 320), (4096, 640, 1280), (1024, 1280, 640), (300, 384, 128), (512, 1152, 320),
+                                   (256, 144, 64), (640, 2560, 192), (16384, 320, 1600)])
+def test_gemm_wide_tiles(M, N, K):
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(DEV).half()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV).half()
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV)
+    lib = L.lib()
+    try:
+        lib.dfb_debug_igemm_force(256, 1)
+        out = gemm(a, w, bias=bias, residual=res)
+        out16 = gemm(a, w, bias=bias, act=1, out_dtype=torch.float16)
+        base = gemm(a, w, bias=bias, residual=res, splits=1) if False else None
+    finally:
+        lib.dfb_debug_igemm_force(0, -1)
+    ref = a.float() @ w.float().t() + bias
+    assert torch.isfinite(out).all() and rel_l2(out, ref + res) < 2e-6
+    assert rel_l2(out16.float(), F.silu(ref)) < 6e-4
+
+
+@pytest.mark.parametrize("B,H,W,C,N", [(2, 16, 64, 320, 320), (4, 8, 32, 128, 640), (3, 4, 16, 64, 192)])
+def test_conv3x3_wide_tiles(B, H, W, C, N):
+    g = torch.Generator(device="cpu").manual_seed(B + H + C + N)
+    a = torch.randn(B, H, W, C, generator=g).to(DEV).half()
+    w = (torch.randn(N, C, 3, 3, generator=g) / math.sqrt(9 * C)).to(DEV).half()
+    bias = torch.randn(N, generator=g).to(DEV)
+    rowvec = torch.randn(B, N, generator=g).to(DEV)
+    res = torch.randn(B, H, W, N, generator=g).to(DEV)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = F.conv2d(a.float().permute(0, 3, 1, 2), w.float(), bias, padding=1)
+        ref = (ref + rowvec[:, :, None, None]).permute(0, 2, 3, 1) + res
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    lib = L.lib()
+    try:
+        lib.dfb_debug_igemm_force(256, 1)
+        out = conv3x3(a, w, bias, rowvec, res, 0)
+    finally:
+        lib.dfb_debug_igemm_force(0, -1)
+    assert torch.isfinite(out).all() and rel_l2(out, ref) < 3e-6
+
+
+@pytest.mark.parametrize("M,C,N", [(2048, 320, 1152), (512, 640, 1920), (300, 192, 384)])
+def test_gemm_layernorm_fold_wide_tiles(M, C, N):
+    lib = L.lib()
+    try:
+        lib.dfb_debug_igemm_force(256, 1)
+        test_gemm_layernorm_fold(M, C, N, 0, 0, 0)
+    finally:
+        lib.dfb_debug_igemm_force(0, -1)

@@ -122,6 +122,10 @@ def main():
                         t = time_candidate(key, b_eff, bn, sp, deep)
                         if t is not None:
                             res[(bn, sp, deep)] = t
+            if not geglu and M >= 1024 and N >= 144:   # wide tiles (128 x up-to-256 columns, 1 CTA / SM, no split-K)
+                t = time_candidate(key, b_eff, 256, 1, 1)
+                if t is not None:
+                    res[(256, 1, 1)] = t
             (bn, sp, deep), t = min(res.items(), key=lambda kv: kv[1])
             total_cur += cur_t * info["count"]
             total_best += min(t, cur_t) * info["count"]
