@@ -32,4 +32,4 @@ if len(sys.argv) > 1:
 else:
     for skip, what in [(0, "normal"), (4, "no global stores"), (2, "no tile finish (phase 2)"), (3, "no staging, no finish")]:
         print(f"DFB_DEBUG_SKIP={skip}: {what}", flush=True)
-        subprocess.run([sys.executable, "tools/_epi_cost.py", "child"] + sys.argv[1:], env=dict(os.environ, DFB_DEBUG_SKIP=str(skip)), timeout=120)
+        subprocess.run([sys.executable, "tools/microbench_epilogue_cost.py", "child"] + sys.argv[1:], env=dict(os.environ, DFB_DEBUG_SKIP=str(skip)), timeout=120)

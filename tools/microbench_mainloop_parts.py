@@ -1,4 +1,9 @@
-"""Which side bounds the main loop of a 1-CTA/SM (deep ring) tile: per-k-block time with parts disabled (DFB_DEBUG_SKIP)."""
+"""Which side bounds the main loop of a 1-CTA/SM (deep ring) tile: per-k-block time with parts disabled.
+
+The DFB_DEBUG_SKIP bits 32 (no MMA instructions), 64 (no activation loads), 128 (no weight loads) this script toggles
+were a temporary instrumentation of the v8 kernel (they cost ~10 % in the hot loops and were removed with the
+rewrite of those loops); profiles/r2_mainloop_bound_before_elect.log is its output on that build.  On the current
+kernel only the un-instrumented line (`python tools/microbench_mainloop_parts.py child`) is meaningful."""
 import os, subprocess, sys
 if len(sys.argv) > 1:
     sys.path.insert(0, ".")
@@ -32,4 +37,4 @@ else:
                        (64 + 32, "no MMA, no A loads"), (128 + 32, "no MMA, no W loads"), (64 + 128 + 32, "no MMA, no loads (barrier round trips only)")]:
         print(f"DFB_DEBUG_SKIP={skip}: {what}", flush=True)
         env = dict(os.environ, DFB_DEBUG_SKIP=str(skip))
-        subprocess.run([sys.executable, "tools/_slope2.py", "child"], env=env, timeout=120)
+        subprocess.run([sys.executable, "tools/microbench_mainloop_parts.py", "child"], env=env, timeout=120)

@@ -1,4 +1,4 @@
-"""One B_eff = 16 level-0 conv (or a Linear) in isolation, for ncu: python tools/_one_conv.py [conv|geglu|lin] [reps]."""
+"""One B_eff = 16 level-0 conv (or a Linear) in isolation, for ncu: python tools/one_gemm_for_ncu.py [conv|geglu|lin] [reps]."""
 import sys
 sys.path.insert(0, ".")
 import torch
