@@ -392,7 +392,8 @@ int groupnorm_launch(const float* src0, int C0, const float* src1, int C1, int B
     const int chunks = C / CW;
     // pixel chunks (= cluster size): aim at >= ~128 CTAs, at least 16 pixels per CTA, registers <= 16 pairs
     int P = 1;
-    while (P < 8 && (long)chunks * B * P < 128 && HW / (P * 2) >= 16) P *= 2;
+    static const int gn_target = getenv("DFB_GN_CTAS") ? atoi(getenv("DFB_GN_CTAS")) : 128;
+    while (P < 8 && (long)chunks * B * P < gn_target && HW / (P * 2) >= 16) P *= 2;
     int NYmax = GN2_THREADS / TX;
     while (P < 8 && (HW + P - 1) / P > NYmax * 16) P *= 2;
     const int px_per = (HW + P - 1) / P;
