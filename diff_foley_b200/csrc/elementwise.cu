@@ -70,15 +70,17 @@ __global__ void upsample2x_f16_kernel(const float4* __restrict__ src, uint2* __r
                                       int H, int W, int C4) {
   pdl_wait();
   pdl_launch_dependents();
-  const size_t total = (size_t)B * 2 * H * 2 * W * C4;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  // (32-bit index arithmetic: the launcher rejects tensors of 2^32 elements or more; 64-bit div / mod cost ~100
+  // instructions each and were most of this kernel)
+  const unsigned total = (unsigned)B * 2u * H * 2u * W * C4;
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned stride = gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
-    const int c = (int)(i % C4);
-    size_t r = i / C4;
-    const int x = (int)(r % (2 * W)); r /= (2 * W);
-    const int y = (int)(r % (2 * H));
-    const int b = (int)(r / (2 * H));
+    const int c = (int)(i % (unsigned)C4);
+    unsigned r = i / (unsigned)C4;
+    const int x = (int)(r % (unsigned)(2 * W)); r /= (unsigned)(2 * W);
+    const int y = (int)(r % (unsigned)(2 * H));
+    const int b = (int)(r / (unsigned)(2 * H));
     const float4 v = src[(((size_t)b * H + (y >> 1)) * W + (x >> 1)) * C4 + c];
     const __half2 a = __floats2half2_rn(v.x, v.y), bb = __floats2half2_rn(v.z, v.w);
     uint2 u;
@@ -95,6 +97,10 @@ int upsample2x_f16_launch(const float* src, __half* dst, int B, int H, int W, in
     return -1;
   }
   const size_t total = (size_t)B * 4 * H * W * (C / 4);
+  if (total >= (1ull << 32) - 148ull * 8 * 256) {
+    set_error("upsample2x: tensor too large for 32-bit indexing");
+    return -1;
+  }
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
   note("upsample2x", 0.0, (double)total * 4 * (2.0 + 1.0));
   DFB_CUDA_OK(launch_pdl(upsample2x_f16_kernel, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const float4*>(src),
@@ -110,16 +116,16 @@ __global__ void im2col_s2_kernel(const float4* __restrict__ src, uint2* __restri
   pdl_wait();
   pdl_launch_dependents();
   const int Ho = H / 2, Wo = W / 2;
-  const size_t total = (size_t)B * Ho * Wo * 9 * C4;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const unsigned total = (unsigned)B * Ho * Wo * 9u * C4;   // (< 2^32: checked by the launcher)
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned stride = gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
-    const int c = (int)(i % C4);
-    size_t r = i / C4;
-    const int tap = (int)(r % 9); r /= 9;
-    const int xo = (int)(r % Wo); r /= Wo;
-    const int yo = (int)(r % Ho);
-    const int b = (int)(r / Ho);
+    const int c = (int)(i % (unsigned)C4);
+    unsigned r = i / (unsigned)C4;
+    const int tap = (int)(r % 9u); r /= 9u;
+    const int xo = (int)(r % (unsigned)Wo); r /= (unsigned)Wo;
+    const int yo = (int)(r % (unsigned)Ho);
+    const int b = (int)(r / (unsigned)Ho);
     const int y = 2 * yo + tap / 3 - 1, x = 2 * xo + tap % 3 - 1;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (y >= 0 && y < H && x >= 0 && x < W) v = src[(((size_t)b * H + y) * W + x) * C4 + c];
@@ -137,6 +143,10 @@ int im2col_s2_launch(const float* src, __half* dst, int B, int H, int W, int C, 
     return -1;
   }
   const size_t total = (size_t)B * (H / 2) * (W / 2) * 9 * (C / 4);
+  if (total >= (1ull << 32) - 148ull * 8 * 256) {
+    set_error("im2col_s2: tensor too large for 32-bit indexing");
+    return -1;
+  }
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
   note("im2col_s2", 0.0, (double)total * 4 * (2.0 + 1.0));
   DFB_CUDA_OK(launch_pdl(im2col_s2_kernel, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const float4*>(src),
